@@ -1,0 +1,257 @@
+/*
+ * gnssb200.h -- C ABI of libgnssb200.so, the B200 (sm_100a) GNSS baseband engine.
+ *
+ * Plain C: pointers, sizes and fixed-width structs only.  Two layers:
+ *
+ *  (1) DROP-IN layer: the exact symbols the reference C receiver binds for its correlator
+ *      (OSG = trunk/GNSS_SOFTWARE_RECEIVERS/POSTPROCESSING_RECEIVERS/osgnss_next_step/src):
+ *        OSG/correlator/correlator.h:4   int REG_read[256], REG_write[256];
+ *        OSG/correlator/correlator.h:8   void correlator_init(double tic_period);
+ *        OSG/correlator/correlator.h:9   void Sim_GP2021_int(char *IF, long nsamp);
+ *      A host program written against correlator.h links against libgnssb200.so instead of
+ *      correlator.c and runs unchanged (INTEGRATION.md shows the link line).
+ *
+ *  (2) BATCHED layer (gnssb200_*): many independent IF streams x 12 channels, closed loop
+ *      (correlator + the integer channel logic of OSG/isr/osgpsisr.c) resident on the GPU, and the
+ *      FFT parallel-code-phase acquisition modelled on SCI/{GPS,GLONASS}/L1/acquisition.sci.
+ *
+ * No CPU fallback exists: every entry point fails (non-zero return, gnssb200_last_error()) when no
+ * CUDA device is usable; the two void drop-in functions print to stderr and abort().
+ */
+#ifndef GNSSB200_H_
+#define GNSSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNSSB200_N_CHANNELS 12 /* OSG/include/globals.h:7 */
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) drop-in layer
+ * ------------------------------------------------------------------------------------------- */
+extern int REG_read[256], REG_write[256]; /* replaces OSG/correlator/correlator.h:4 (library owns them) */
+
+/* replaces OSG/correlator/correlator.c:107-132.  Also writes the host program's globals
+ * Carrier_DCO_Delta, Code_DCO_Delta, gps_code_ref, gps_carrier_ref, glonass_code_ref,
+ * glonass_carrier_ref, d_freq (OSG/include/globals.h:38-49) when the host defines them (weak refs),
+ * reading freq_bin_width (globals.h:54) the same way. */
+void correlator_init(double tic_period);
+
+/* replaces OSG/correlator/correlator.c:148-316.  IF: host buffer of 2*nsamp int8 (I,Q interleaved),
+ * or nsamp int8 when the host global use_iq_processing (globals.h:56) is 0.  Synchronous: REG_read /
+ * REG_write are up to date on return; IF may be overwritten afterwards. */
+void Sim_GP2021_int(char *IF, long nsamp);
+
+/* 0 = ok; otherwise the cudaError_t (or a negative library code) of the most recent failure. */
+int gnssb200_last_error(void);
+const char *gnssb200_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) batched layer -- tracking
+ * ------------------------------------------------------------------------------------------- */
+
+/* Receiver constants.  Mirrors the tunable globals of OSG/include/globals.h:7-63 plus the values
+ * correlator_init / init_tracking_loops_parameter derive from them. */
+typedef struct gnssb200_cfg {
+  double samp_rate;        /* SAMP_RATE 16e6                      globals.h:12 */
+  double clock_mult;       /* SYSTEM_CLOCK_MULTIPLIER 5           globals.h:13 */
+  double gps_carrier_if;   /* GPS_CARRIER_IF 2.42e6               globals.h:16 */
+  double gps_code_f;       /* GPS_CODE_F 1023000                  globals.h:17 */
+  double freq_bin_width;   /* 1000 Hz                             globals.h:54 */
+  double tic_period;       /* value passed to correlator_init (the stock main passes int 0) */
+  int32_t carrier_nco_bits;/* CARRIER_NCO_DIGIT_CAPACITY 30       globals.h:20 */
+  int32_t code_nco_bits;   /* CODE_NCO_DIGIT_CAPACITY 29          globals.h:21 */
+  int32_t acq_thresh;      /* 1800                                globals.h:36 */
+  int32_t interr_int_us;   /* 512                                 globals.h:51 */
+  int64_t Bnp, Bnf, Bnd;   /* 25, 1400, 2                         globals.h:59-61 */
+  int64_t pll_integ_ms, dll_integ_ms; /* 1, 1                     globals.h:62-63 */
+  /* derived (filled by gnssb200_cfg_derive; same arithmetic as the reference) */
+  int64_t gps_carrier_ref, gps_code_ref, d_freq;   /* correlator.c:114-121 */
+  int64_t tic_ref;                                 /* correlator.c:124 */
+  int32_t pll_i1, pll_i2, pll_i3, dll_i1, dll_i2;  /* osgpsisr.c:252-342 */
+} gnssb200_cfg;
+
+void gnssb200_cfg_default(gnssb200_cfg *cfg); /* reference defaults (globals.h) */
+void gnssb200_cfg_derive(gnssb200_cfg *cfg);  /* correlator_init + init_tracking_loops_parameter */
+
+/* Per-channel host-side logic state: the fields of struct tracking_channel
+ * (OSG/include/structs.h:86-128) that the acquisition/confirm/pull-in/track state machine uses.
+ * C 'long' is int64 here (the oracle is the LP64 build of the reference). */
+typedef struct gnssb200_chan {
+  int32_t state;            /* tracking_enum: 0 off 1 acq 2 confirm 3 pull-in 4 tracking */
+  int16_t accum[6];         /* i_prompt q_prompt i_late q_late i_early q_early (structs.h:54-61) */
+  int16_t prev_accum[6];
+  int64_t mean_early, mean_prompt, mean_late; /* accum_mean */
+  int64_t cross, dot;
+  int64_t carrError, oldCarrError, freqError;
+  int64_t carrNco, oldCarrNco, carrFreq, carrFreqBasis;
+  int64_t codeError, oldCodeError, codeFreq, codeFreqBasis, codeNco, oldCodeNco;
+  int64_t ch_time;
+  int32_t n_freq, i_confirm, n_thresh, codes, del_freq;
+  int32_t CN0;
+  int64_t carrier_freq, carrier_cold_corr;
+  int32_t sign_pos, prev_sign_pos, sign_count;
+  int32_t ms_count, ms_set;
+  uint64_t ms_sign;
+  int32_t bit;
+  int32_t search_max_PRN_delay, search_max_f;
+  int32_t pad_;
+} gnssb200_chan;
+
+/* Per-channel correlator state: struct gp2021_channel + ms/bit counters
+ * (OSG/correlator/correlator.c:33,36-47). */
+typedef struct gnssb200_corr {
+  uint32_t carrier_phase, carrier_cycle, code_phase;
+  uint32_t half_chip;       /* uint16_t in the reference */
+  int32_t acc[6];           /* order of REG_read offsets: IL QL IP QP IE QE (correlator.c:15-20) */
+  int32_t ms_counter, bit_counter;
+} gnssb200_corr;
+
+/* Everything one receiver (one IF stream) owns. */
+typedef struct gnssb200_rx {
+  int32_t reg_read[256];
+  int32_t reg_write[256];
+  gnssb200_corr corr[GNSSB200_N_CHANNELS];
+  gnssb200_chan chan[GNSSB200_N_CHANNELS];
+  int64_t tic;              /* correlator.c:30 (tic_ref lives in cfg) */
+  int64_t blocks_done;      /* number of Sim_GP2021_int-equivalent blocks processed so far */
+  int32_t halted;           /* 1 once a dumping channel was found in CHANNEL_OFF (osgpsisr.c:383-386: exit(0)) */
+  int32_t pad_;
+} gnssb200_rx;
+
+/* One record per correlator dump (one per channel per code period). */
+typedef struct gnssb200_dump {
+  int32_t block;            /* index of the block (Sim_GP2021_int call) in which the dump fell */
+  int16_t ch;
+  int16_t state;            /* chan.state AFTER gpsisr handled this dump */
+  int32_t acc[6];           /* IL QL IP QP IE QE, full int32 as stored in REG_read */
+  uint32_t carrier_incr;    /* (REG_write[+3]<<16)+REG_write[+4] after gpsisr */
+  uint32_t code_incr;       /* (REG_write[+5]<<16)+REG_write[+6] after gpsisr */
+  int16_t n_freq;
+  int16_t codes;
+  int32_t slew;             /* REG_write[ch*8+0x84] after gpsisr */
+} gnssb200_dump;            /* 48 bytes */
+
+/* Host helpers that mirror the reference's register accessors on a gnssb200_rx
+ * (OSG/gp2021/gp2021.c:74-130): same masking to 16 bits, same <<(32-N) * 5 scaling. */
+void gnssb200_rx_init(gnssb200_rx *rx, const gnssb200_cfg *cfg); /* zero + correlator_init state */
+void gnssb200_rx_cold_allocate(gnssb200_rx *rx, const gnssb200_cfg *cfg,
+                               const int32_t prn[GNSSB200_N_CHANNELS]); /* osgnss_next_step.c:41-84 */
+void gnssb200_ch_cntl(gnssb200_rx *rx, int ch, int data);
+void gnssb200_ch_carrier(gnssb200_rx *rx, const gnssb200_cfg *cfg, int ch, int64_t freq);
+void gnssb200_ch_code(gnssb200_rx *rx, const gnssb200_cfg *cfg, int ch, int64_t freq);
+void gnssb200_ch_code_slew(gnssb200_rx *rx, int ch, int data);
+void gnssb200_ch_epoch_load(gnssb200_rx *rx, int ch, unsigned data);
+
+typedef struct gnssb200_handle gnssb200_handle;
+
+#define GNSSB200_FMT_INT8_IQ   0 /* int8 I,Q interleaved: 2 bytes / complex sample */
+#define GNSSB200_FMT_PACKED2   1 /* 2+2 bit: I0 Q0 I1 Q1 in one byte, LSB first, code {0:+1,1:-1,2:+3,3:-3} */
+#define GNSSB200_FMT_INT8_I    2 /* int8 real samples (use_iq_processing = 0 path, correlator.c:217-224) */
+
+/* device: CUDA device ordinal.  Returns NULL on failure (see gnssb200_last_error). */
+gnssb200_handle *gnssb200_open(int device, const gnssb200_cfg *cfg);
+void gnssb200_close(gnssb200_handle *h);
+
+/* Number of receivers (streams) resident on the device; (re)allocates device state. */
+int gnssb200_set_streams(gnssb200_handle *h, int n_streams);
+int gnssb200_upload_rx(gnssb200_handle *h, int first, int count, const gnssb200_rx *rx);
+int gnssb200_download_rx(gnssb200_handle *h, int first, int count, gnssb200_rx *rx);
+
+/* Closed-loop tracking / serial search on device memory.
+ *   d_if          device pointer; stream s starts at d_if + s*stream_stride_bytes
+ *   fmt           GNSSB200_FMT_*
+ *   nsamp         complex samples per block (the reference uses 8192 = 512 us, osgnss_next_step.c:150)
+ *   nblocks       blocks to process per stream (each = one Sim_GP2021_int + gpsisr of the reference)
+ *   d_dumps       device buffer of n_streams*12*dump_cap records, or NULL; channel (s,ch) writes at
+ *                 [(s*12+ch)*dump_cap + k]
+ *   d_dump_count  device int32[n_streams*12], number of records written per channel (may be NULL)
+ *   cuda_stream   a cudaStream_t passed as void* (NULL = default stream).  Asynchronous.
+ * Blocks continue from the state left by the previous call (rx.blocks_done advances). */
+int gnssb200_track_run(gnssb200_handle *h, const void *d_if, size_t stream_stride_bytes, int fmt,
+                       int nsamp, int64_t nblocks, gnssb200_dump *d_dumps, int dump_cap,
+                       int32_t *d_dump_count, void *cuda_stream);
+
+/* Convenience: same from host memory (copies in, runs, copies records out, synchronises). */
+int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stream_stride_bytes, int fmt,
+                            int nsamp, int64_t nblocks, gnssb200_dump *h_dumps, int dump_cap,
+                            int32_t *h_dump_count);
+
+/* Number of kernels this library has launched since open (bench.py reports it as gpu_launches). */
+int64_t gnssb200_launch_count(const gnssb200_handle *h);
+/* Device time (ms, CUDA events on the launching stream) of the most recent track/acq kernel
+ * sequence; valid after the stream was synchronised. */
+float gnssb200_last_kernel_ms(gnssb200_handle *h);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) batched layer -- FFT parallel-code-phase acquisition
+ *     modelled on acqResults = acquisition(longSignal, settings)
+ *     SCI/GLONASS/L1/acquisition.sci:1-198, SCI/GPS/L1/acquisition.sci
+ * ------------------------------------------------------------------------------------------- */
+#define GNSSB200_SYS_GPS     0
+#define GNSSB200_SYS_GLONASS 1
+
+typedef struct gnssb200_acq_cfg {
+  int32_t system;           /* GNSSB200_SYS_* : code table + exclusion-window rule (GPS '>' / GLONASS '>=') */
+  double samp_freq;         /* settings.samplingFreq   16e6 */
+  double IF;                /* settings.IF             GPS 2.42e6 / GLONASS 1e6 */
+  double IF_step;           /* settings.L1_IF_step     GLONASS 562500, GPS 0 */
+  double code_freq;         /* settings.codeFreqBasis  1.023e6 / 0.511e6 */
+  int32_t code_length;      /* settings.codeLength     1023 / 511 */
+  double search_band_khz;   /* settings.acqSearchBand */
+  int32_t coh_ms;           /* settings.acqCohIntegration */
+  int32_t n_noncoh;         /* 0/1: stock "better of two blocks"; K>=2: sum of K consecutive blocks (config 4) */
+  double threshold;         /* settings.acqThreshold   3.0 */
+  int32_t n_sv;             /* entries in sv[] */
+  int32_t sv[64];           /* PRN list (GPS) or frequency-channel list k=-7..6 (GLONASS) */
+  /* partition of the (sv, bin) grid for multi-GPU runs: this process handles global rows
+   * r with r % part_count == part_index, r = sv_index*n_bins + bin */
+  int32_t part_index, part_count;
+} gnssb200_acq_cfg;
+
+typedef struct gnssb200_acq_row {   /* one (sv, Doppler bin) row of the search grid */
+  float peak;               /* max over code phases of the kept block */
+  int32_t code_phase;       /* 0-based first argmax (Scilab's is this + 1) */
+  float second;             /* max outside +-1 chip around this row's own argmax (reference rule) */
+  int32_t block;            /* which block was kept (0/1); 0 for non-coherent mode */
+} gnssb200_acq_row;
+
+typedef struct gnssb200_acq_result { /* one per sv, layout of acqResults */
+  double carrFreq;          /* 0 when below threshold */
+  int32_t codePhase;        /* 1-based, 0 when below threshold */
+  int32_t sv;               /* PRN / frequency channel (freqChannel); 0 when below threshold */
+  double peakMetric;
+  int32_t bin;              /* 1-based frequencyBinIndex of the peak (always filled) */
+  int32_t codePhaseRaw;     /* 1-based code phase of the peak (always filled) */
+  float peak, second;
+} gnssb200_acq_result;
+
+/* Number of Doppler bins for a configuration: round(band*2*Tcoh)+1 (acquisition.sci:66-67). */
+int gnssb200_acq_num_bins(const gnssb200_acq_cfg *cfg);
+/* Samples the record must hold: n_noncoh<=1 -> 2*coh_ms ms, else n_noncoh*coh_ms ms. */
+int64_t gnssb200_acq_samples_needed(const gnssb200_acq_cfg *cfg);
+
+/* Grid search on a device-resident int8 I,Q record (fmt INT8_IQ or PACKED2).
+ *   d_rows   device buffer [n_sv * n_bins] of rows; only this partition's rows are written
+ *            (others keep peak = -1).  Multi-GPU callers all-gather this table (NCCL) and then call
+ *            gnssb200_acq_finalize on the merged table.
+ * Asynchronous on cuda_stream. */
+int gnssb200_acq_search(gnssb200_handle *h, const gnssb200_acq_cfg *cfg, const void *d_iq, int fmt,
+                        int64_t n_samples, gnssb200_acq_row *d_rows, void *cuda_stream);
+
+/* Peak / second-peak / threshold logic of acquisition.sci:145-191 on a complete host row table. */
+int gnssb200_acq_finalize(const gnssb200_acq_cfg *cfg, const gnssb200_acq_row *h_rows,
+                          gnssb200_acq_result *results /* [n_sv] */);
+
+/* Convenience: host record in, results out (search + finalize, single GPU, synchronises). */
+int gnssb200_acq_pcps_host(gnssb200_handle *h, const gnssb200_acq_cfg *cfg, const void *h_iq, int fmt,
+                           int64_t n_samples, gnssb200_acq_result *results, gnssb200_acq_row *h_rows_opt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNSSB200_H_ */
