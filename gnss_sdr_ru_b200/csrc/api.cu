@@ -1,0 +1,371 @@
+// api.cu -- C ABI of libgnssb200.so (include/gnssb200.h): handle management, host-side register
+// helpers, the batched tracking entry points and the drop-in correlator symbols of the reference
+// (OSG/correlator/correlator.h:4,8,9).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local int g_err_code = 0;
+static thread_local char g_err_text[512] = "";
+
+void gnssb200_set_error(int code, const char *what, const char *file, int line) {
+  g_err_code = code;
+  snprintf(g_err_text, sizeof g_err_text, "%s (%s:%d)", what, file, line);
+}
+extern "C" int gnssb200_last_error(void) { return g_err_code; }
+extern "C" const char *gnssb200_last_error_string(void) { return g_err_text; }
+
+// ---------------------------------------------------------------------------------------------
+// configuration: OSG/include/globals.h defaults; correlator_init (correlator.c:107-125);
+// init_tracking_loops_parameter (osgnss_next_step.c:99-107 -> osgpsisr.c:252-342)
+extern "C" void gnssb200_cfg_default(gnssb200_cfg *c) {
+  memset(c, 0, sizeof *c);
+  c->samp_rate = 16.0e6;
+  c->clock_mult = 5.0;
+  c->gps_carrier_if = 2.42e6;
+  c->gps_code_f = 1023000.0;
+  c->freq_bin_width = 1000.0;
+  c->tic_period = 0.0;
+  c->carrier_nco_bits = 30;
+  c->code_nco_bits = 29;
+  c->acq_thresh = 1800;
+  c->interr_int_us = 512;
+  c->Bnp = 25;
+  c->Bnf = 1400;
+  c->Bnd = 2;
+  c->pll_integ_ms = 1;
+  c->dll_integ_ms = 1;
+}
+
+extern "C" void gnssb200_cfg_derive(gnssb200_cfg *c) {
+  const double carr_res = c->clock_mult * c->samp_rate / pow(2.0, (double)c->carrier_nco_bits);
+  const double code_res = c->clock_mult * c->samp_rate / pow(2.0, (double)c->code_nco_bits);
+  c->gps_code_ref = (int64_t)(c->gps_code_f / code_res);
+  c->gps_carrier_ref = (int64_t)(c->gps_carrier_if / carr_res);
+  c->d_freq = (int64_t)((double)(int)c->freq_bin_width / carr_res);
+  c->tic_ref = (int64_t)(c->samp_rate * c->tic_period);
+  const double a2 = 1.414;
+  {
+    const double wp = (double)c->Bnp / 0.53, wf = (double)c->Bnf / 0.25, T = (double)c->pll_integ_ms / 1000;
+    const double scale = (double)(1 << c->carrier_nco_bits) / (c->samp_rate * c->clock_mult);
+    c->pll_i1 = (int32_t)((T * (wp * wp) + a2 * wp) * scale);
+    c->pll_i2 = (int32_t)((a2 * wp) * scale);
+    c->pll_i3 = (int32_t)((T * wf) * scale);
+  }
+  {
+    const double w = (double)c->Bnd / 0.53, T = (double)c->dll_integ_ms / 1000;
+    const double scale = (double)(1 << c->code_nco_bits) / (c->samp_rate * c->clock_mult);
+    c->dll_i1 = (int32_t)((T * (w * w) + a2 * w) * scale);
+    c->dll_i2 = (int32_t)((a2 * w) * scale);
+  }
+}
+
+// register accessors on a host-side gnssb200_rx (OSG/gp2021/gp2021.c:11-14,74-130)
+static inline void host_put16(gnssb200_rx *rx, int addr, int data) { rx->reg_write[addr & 0xff] = (int)(uint16_t)data; }
+extern "C" void gnssb200_ch_cntl(gnssb200_rx *rx, int ch, int data) { host_put16(rx, ch << 3, data); }
+extern "C" void gnssb200_ch_code_slew(gnssb200_rx *rx, int ch, int data) { host_put16(rx, (ch << 3) + 0x84, data); }
+extern "C" void gnssb200_ch_epoch_load(gnssb200_rx *rx, int ch, unsigned data) { host_put16(rx, (ch << 3) + 7, (int)data); }
+static void host_put_nco(gnssb200_rx *rx, int addr, int64_t freq, int bits, double mult) {
+  int64_t w = freq << (32 - bits);
+  w = (int64_t)((double)w * mult);
+  host_put16(rx, addr, (int)(w >> 16));
+  host_put16(rx, addr + 1, (int)(w & 0xffff));
+}
+extern "C" void gnssb200_ch_carrier(gnssb200_rx *rx, const gnssb200_cfg *c, int ch, int64_t freq) {
+  host_put_nco(rx, (ch << 3) + 3, freq, c->carrier_nco_bits, c->clock_mult);
+}
+extern "C" void gnssb200_ch_code(gnssb200_rx *rx, const gnssb200_cfg *c, int ch, int64_t freq) {
+  host_put_nco(rx, (ch << 3) + 5, freq, c->code_nco_bits, c->clock_mult);
+}
+extern "C" void gnssb200_rx_init(gnssb200_rx *rx, const gnssb200_cfg *c) {
+  memset(rx, 0, sizeof *rx);
+  rx->tic = c->tic_ref;
+}
+extern "C" void gnssb200_rx_cold_allocate(gnssb200_rx *rx, const gnssb200_cfg *c, const int32_t prn[GNSSB200_N_CHANNELS]) {
+  for (int ch = 0; ch < NCH; ch++) {
+    gnssb200_chan *k = &rx->chan[ch];
+    gnssb200_ch_cntl(rx, ch, 0);
+    gnssb200_ch_carrier(rx, c, ch, c->gps_carrier_ref);
+    gnssb200_ch_code(rx, c, ch, c->gps_code_ref);
+    k->state = 1;
+    k->carrier_cold_corr = 0;
+    k->del_freq = 1;
+    k->n_freq = 0;
+    k->search_max_PRN_delay = 2045;
+    k->search_max_f = 5;
+    k->ms_set = 0;
+  }
+  for (int ch = 0; ch < NCH; ch++)
+    if (prn[ch] > 0) gnssb200_ch_cntl(rx, ch, prn[ch]);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" gnssb200_handle *gnssb200_open(int device, const gnssb200_cfg *cfg) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    gnssb200_set_error(e != cudaSuccess ? (int)e : -1, "no CUDA device (libgnssb200 has no CPU path)", __FILE__, __LINE__);
+    return nullptr;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    return nullptr;
+  }
+  gnssb200_handle *h = new gnssb200_handle();
+  memset(h, 0, sizeof *h);
+  h->device = device;
+  if (cfg)
+    h->cfg = *cfg;
+  else {
+    gnssb200_cfg_default(&h->cfg);
+    gnssb200_cfg_derive(&h->cfg);
+  }
+  std::vector<uint32_t> table(TABLE_ENTRIES + 1);
+  build_code_table_host(table.data());
+  if ((e = cudaMalloc(&h->d_code_table, table.size() * 4)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_code_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+    gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+extern "C" void gnssb200_close(gnssb200_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  acq_free_workspace(h);
+  cudaFree(h->d_rx);
+  cudaFree(h->d_chan_flags);
+  cudaFree(h->d_code_table);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+extern "C" int gnssb200_set_streams(gnssb200_handle *h, int n) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (n == h->n_streams) return 0;
+  cudaFree(h->d_rx);
+  cudaFree(h->d_chan_flags);
+  h->d_rx = nullptr;
+  h->d_chan_flags = nullptr;
+  h->n_streams = 0;
+  if (n > 0) {
+    CUDA_TRY(cudaMalloc(&h->d_rx, sizeof(gnssb200_rx) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&h->d_chan_flags, sizeof(int32_t) * NCH * (size_t)n));
+    CUDA_TRY(cudaMemset(h->d_rx, 0, sizeof(gnssb200_rx) * (size_t)n));
+    CUDA_TRY(cudaMemset(h->d_chan_flags, 0, sizeof(int32_t) * NCH * (size_t)n));
+    h->n_streams = n;
+  }
+  return 0;
+}
+
+static int check_range(gnssb200_handle *h, int first, int count) {
+  if (first < 0 || count < 0 || first + count > h->n_streams) {
+    gnssb200_set_error(-2, "stream range outside gnssb200_set_streams()", __FILE__, __LINE__);
+    return -2;
+  }
+  return 0;
+}
+extern "C" int gnssb200_upload_rx(gnssb200_handle *h, int first, int count, const gnssb200_rx *rx) {
+  if (check_range(h, first, count)) return -2;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(h->d_rx + first, rx, sizeof(gnssb200_rx) * (size_t)count, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int gnssb200_download_rx(gnssb200_handle *h, int first, int count, gnssb200_rx *rx) {
+  if (check_range(h, first, count)) return -2;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(rx, h->d_rx + first, sizeof(gnssb200_rx) * (size_t)count, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int64_t gnssb200_launch_count(const gnssb200_handle *h) { return h->launches; }
+
+extern "C" float gnssb200_last_kernel_ms(gnssb200_handle *h) {
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+static size_t fmt_bytes(int fmt, long long nsamples) {
+  return fmt == GNSSB200_FMT_INT8_IQ ? (size_t)nsamples * 2 : (fmt == GNSSB200_FMT_PACKED2 ? (size_t)nsamples / 2 : (size_t)nsamples);
+}
+
+extern "C" int gnssb200_track_run(gnssb200_handle *h, const void *d_if, size_t stride, int fmt, int nsamp, int64_t nblocks,
+                                  gnssb200_dump *d_dumps, int dump_cap, int32_t *d_dump_count, void *cuda_stream) {
+  if (!h || h->n_streams <= 0) {
+    gnssb200_set_error(-3, "gnssb200_track_run: no streams configured", __FILE__, __LINE__);
+    return -3;
+  }
+  if (fmt < 0 || fmt > 2 || nsamp <= 0 || (fmt == GNSSB200_FMT_PACKED2 && (nsamp & 1))) {
+    gnssb200_set_error(-4, "gnssb200_track_run: bad format / block size", __FILE__, __LINE__);
+    return -4;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CUDA_TRY(cudaEventRecord(h->ev0, st));
+  int rc = track_launch(h, 0, h->n_streams, d_if, stride, fmt, nsamp, nblocks, 1, d_dumps, dump_cap, d_dump_count, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev1, st));
+  return 0;
+}
+
+extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stride, int fmt, int nsamp, int64_t nblocks,
+                                       gnssb200_dump *h_dumps, int dump_cap, int32_t *h_dump_count) {
+  if (!h || h->n_streams <= 0) {
+    gnssb200_set_error(-3, "gnssb200_track_run_host: no streams configured", __FILE__, __LINE__);
+    return -3;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int S = h->n_streams;
+  const size_t per_stream = fmt_bytes(fmt, (long long)nsamp * nblocks);
+  const size_t dstride = (per_stream + 255) & ~(size_t)255;
+  uint8_t *d_if = nullptr;
+  gnssb200_dump *d_dumps = nullptr;
+  int32_t *d_cnt = nullptr;
+  CUDA_TRY(cudaMalloc(&d_if, dstride * S + 256));
+  CUDA_TRY(cudaMemcpy2D(d_if, dstride, h_if, stride, per_stream, S, cudaMemcpyHostToDevice));
+  const bool want = h_dumps && dump_cap > 0;
+  if (want) {
+    CUDA_TRY(cudaMalloc(&d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap));
+    CUDA_TRY(cudaMalloc(&d_cnt, sizeof(int32_t) * S * NCH));
+    if (h_dump_count)
+      CUDA_TRY(cudaMemcpy(d_cnt, h_dump_count, sizeof(int32_t) * S * NCH, cudaMemcpyHostToDevice));
+    else
+      CUDA_TRY(cudaMemset(d_cnt, 0, sizeof(int32_t) * S * NCH));
+  }
+  int rc = gnssb200_track_run(h, d_if, dstride, fmt, nsamp, nblocks, d_dumps, want ? dump_cap : 0, d_cnt, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+      rc = (int)e;
+    }
+  }
+  if (!rc && want) {
+    cudaMemcpy(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost);
+    if (h_dump_count) cudaMemcpy(h_dump_count, d_cnt, sizeof(int32_t) * S * NCH, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_if);
+  cudaFree(d_dumps);
+  cudaFree(d_cnt);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// drop-in layer: the reference's own correlator symbols
+extern "C" {
+int REG_read[256], REG_write[256];
+
+// globals the reference's host program defines under '#define MAIN' (OSG/include/globals.h:38-56).
+// Weak: present when linked into the reference receiver, absent when loaded through ctypes.
+extern double Carrier_DCO_Delta __attribute__((weak));
+extern double Code_DCO_Delta __attribute__((weak));
+extern long gps_code_ref __attribute__((weak));
+extern long gps_carrier_ref __attribute__((weak));
+extern long glonass_code_ref __attribute__((weak));
+extern long glonass_carrier_ref __attribute__((weak));
+extern long d_freq __attribute__((weak));
+extern double freq_bin_width __attribute__((weak));
+extern int use_iq_processing __attribute__((weak));
+}
+
+struct DropIn {
+  gnssb200_handle *h = nullptr;
+  uint8_t *d_if = nullptr, *h_if = nullptr;  // staging (pinned host / device)
+  size_t if_cap = 0;
+  int32_t *h_regs = nullptr;                 // pinned 512 ints: reg_read | reg_write
+  cudaStream_t st = nullptr;
+};
+static DropIn g_drop;
+
+[[noreturn]] static void dropin_die(const char *where) {
+  fprintf(stderr, "libgnssb200: %s failed: %s -- no CPU fallback, aborting\n", where, gnssb200_last_error_string());
+  abort();
+}
+
+extern "C" void correlator_init(double tic_period) {
+  gnssb200_cfg cfg;
+  gnssb200_cfg_default(&cfg);
+  cfg.tic_period = tic_period;
+  if (&freq_bin_width) cfg.freq_bin_width = freq_bin_width;
+  gnssb200_cfg_derive(&cfg);
+  // what correlator.c:110-121 leaves in the host's globals
+  if (&Carrier_DCO_Delta) Carrier_DCO_Delta = cfg.clock_mult * cfg.samp_rate / pow(2.0, (double)cfg.carrier_nco_bits);
+  if (&Code_DCO_Delta) Code_DCO_Delta = cfg.clock_mult * cfg.samp_rate / pow(2.0, (double)cfg.code_nco_bits);
+  if (&gps_code_ref) gps_code_ref = (long)cfg.gps_code_ref;
+  if (&gps_carrier_ref) gps_carrier_ref = (long)cfg.gps_carrier_ref;
+  if (&glonass_code_ref) glonass_code_ref = (long)(511000.0 / (cfg.clock_mult * cfg.samp_rate / pow(2.0, (double)cfg.code_nco_bits)));
+  if (&glonass_carrier_ref) glonass_carrier_ref = (long)(0.0e6 / (cfg.clock_mult * cfg.samp_rate / pow(2.0, (double)cfg.carrier_nco_bits)));
+  if (&d_freq) d_freq = (long)cfg.d_freq;
+
+  if (g_drop.h) {
+    gnssb200_close(g_drop.h);
+    g_drop.h = nullptr;
+  }
+  const char *dev = getenv("GNSSB200_DEVICE");
+  g_drop.h = gnssb200_open(dev ? atoi(dev) : 0, &cfg);
+  if (!g_drop.h) dropin_die("gnssb200_open");
+  if (gnssb200_set_streams(g_drop.h, 1)) dropin_die("gnssb200_set_streams");
+  gnssb200_rx *rx = new gnssb200_rx;
+  gnssb200_rx_init(rx, &cfg);  // memset(gpchan) + tic = tic_ref (correlator.c:124-128)
+  memcpy(rx->reg_read, REG_read, sizeof REG_read);
+  memcpy(rx->reg_write, REG_write, sizeof REG_write);
+  int rc = gnssb200_upload_rx(g_drop.h, 0, 1, rx);
+  delete rx;
+  if (rc) dropin_die("gnssb200_upload_rx");
+  if (!g_drop.st && cudaStreamCreateWithFlags(&g_drop.st, cudaStreamNonBlocking) != cudaSuccess) dropin_die("cudaStreamCreate");
+  if (!g_drop.h_regs && cudaMallocHost(&g_drop.h_regs, 2048) != cudaSuccess) dropin_die("cudaMallocHost");
+}
+
+extern "C" void Sim_GP2021_int(char *IF, long nsamp) {
+  DropIn &d = g_drop;
+  if (!d.h) {
+    gnssb200_set_error(-5, "Sim_GP2021_int before correlator_init", __FILE__, __LINE__);
+    dropin_die("Sim_GP2021_int");
+  }
+  if (nsamp <= 0) {  // the reference's loops simply do not run; status words are still rewritten
+    REG_read[0x82] = 0;
+    return;
+  }
+  const int fmt = (&use_iq_processing && !use_iq_processing) ? GNSSB200_FMT_INT8_I : GNSSB200_FMT_INT8_IQ;
+  const size_t bytes = fmt_bytes(fmt, nsamp);
+  cudaError_t e;
+  if (bytes > d.if_cap) {
+    cudaFree(d.d_if);
+    cudaFreeHost(d.h_if);
+    d.if_cap = (bytes + 4095) & ~(size_t)4095;
+    if ((e = cudaMalloc(&d.d_if, d.if_cap)) != cudaSuccess || (e = cudaMallocHost(&d.h_if, d.if_cap)) != cudaSuccess) {
+      gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+      dropin_die("staging allocation");
+    }
+  }
+  memcpy(d.h_if, IF, bytes);
+  memcpy(d.h_regs, REG_read, 1024);
+  memcpy(d.h_regs + 256, REG_write, 1024);
+  // reg_read | reg_write are the first 2 KiB of gnssb200_rx
+  e = cudaMemcpyAsync(d.h->d_rx, d.h_regs, 2048, cudaMemcpyHostToDevice, d.st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d.d_if, d.h_if, bytes, cudaMemcpyHostToDevice, d.st);
+  if (e != cudaSuccess) {
+    gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    dropin_die("H2D copy");
+  }
+  if (track_launch(d.h, 0, 1, d.d_if, 0, fmt, (int)nsamp, 1, /*run_isr=*/0, nullptr, 0, nullptr, d.st)) dropin_die("track_launch");
+  e = cudaMemcpyAsync(d.h_regs, d.h->d_rx, 2048, cudaMemcpyDeviceToHost, d.st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.st);
+  if (e != cudaSuccess) {
+    gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    dropin_die("kernel / D2H copy");
+  }
+  memcpy(REG_read, d.h_regs, 1024);
+  memcpy(REG_write, d.h_regs + 256, 1024);
+}

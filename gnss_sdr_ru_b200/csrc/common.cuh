@@ -1,0 +1,45 @@
+// common.cuh -- shared declarations of libgnssb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gnssb200.h"
+
+#define NCH GNSSB200_N_CHANNELS
+#define HALF_CHIPS 2046
+#define TABLE_ROWS 34                       // rows 0 and 33 are zero
+#define TABLE_ENTRIES (TABLE_ROWS * HALF_CHIPS)
+
+// library-wide error slot (api.cu)
+void gnssb200_set_error(int code, const char *what, const char *file, int line);
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      gnssb200_set_error((int)e__, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return (int)e__;                                                        \
+    }                                                                         \
+  } while (0)
+
+struct gnssb200_handle {
+  int device;
+  gnssb200_cfg cfg;
+  int n_streams;
+  gnssb200_rx *d_rx;          // [n_streams]
+  int32_t *d_chan_flags;      // [n_streams*12] bit0: dumped in the last block, bit1: halted
+  uint32_t *d_code_table;     // [TABLE_ENTRIES+1] packed E | P<<8 | L<<16 (int8 each), last entry 0
+  cudaEvent_t ev0, ev1;
+  long long launches;
+  // acquisition workspace (acq.cu)
+  void *acq_ws;
+};
+
+// track.cu
+int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void *d_if, size_t stride, int fmt,
+                 int nsamp, long long nblocks, int run_isr, gnssb200_dump *d_dumps, int dump_cap,
+                 int32_t *d_dump_count, cudaStream_t st);
+void build_code_table_host(uint32_t *table /* TABLE_ENTRIES+1 */);
+
+// acq.cu
+void acq_free_workspace(gnssb200_handle *h);

@@ -1,0 +1,258 @@
+// isr_device.cuh -- the per-dump integer channel logic of the reference, executed by one lane per
+// (stream, channel) right after the correlator reduction so the loop closes on the device.
+//
+// Follows OSG/isr/osgpsisr.c (OSG = trunk/GNSS_SOFTWARE_RECEIVERS/POSTPROCESSING_RECEIVERS/
+// osgnss_next_step/src): gpsisr :360-408, ch_acq :424-459, ch_confirm :475-518, ch_pull_in :535-673,
+// ch_track :692-768, rss :77-91, sqrt_newton :148-178, fix_atan2 :199-231, and the register
+// accessors OSG/gp2021/gp2021.c:11-28,74-130.  C `long` is int64_t (LP64 semantics).
+// Channels only touch their own registers, so each channel's lane owns a private register view.
+#pragma once
+#include "common.cuh"
+
+// The slice of REG_write / REG_read that belongs to one channel.
+struct ChRegs {
+  int w_prn;        // REG_write[ch*8+0]
+  int w_carr_hi;    // +3
+  int w_carr_lo;    // +4
+  int w_code_hi;    // +5
+  int w_code_lo;    // +6
+  int w_epoch;      // +7
+  int w_slew;       // REG_write[ch*8+0x84]
+  int r_meas[8];    // REG_read[ch*8+0..7]   (1..6 TIC latches, 7 epoch)
+  int r_acc[6];     // REG_read[ch*8+0x84+0..5]  IL QL IP QP IE QE
+};
+
+__device__ __forceinline__ int reg16(int v) { return (int)(uint16_t)v; }  // outpwd(): unsigned short
+
+__device__ __forceinline__ void dev_put_nco(int &hi, int &lo, long long freq, int bits, double mult) {
+  long long w = freq << (32 - bits);
+  w = (long long)((double)w * mult);  // gp2021.c:90-91 / 109-110
+  hi = reg16((int)(w >> 16));
+  lo = reg16((int)(w & 0xffff));
+}
+__device__ __forceinline__ void dev_ch_carrier(ChRegs &r, const gnssb200_cfg &c, long long f) {
+  dev_put_nco(r.w_carr_hi, r.w_carr_lo, f, c.carrier_nco_bits, c.clock_mult);
+}
+__device__ __forceinline__ void dev_ch_code(ChRegs &r, const gnssb200_cfg &c, long long f) {
+  dev_put_nco(r.w_code_hi, r.w_code_lo, f, c.code_nco_bits, c.clock_mult);
+}
+
+__device__ __forceinline__ long long dev_abs_trunc(long long v) {  // int abs() applied to a long
+  int t = (int)v;
+  return (long long)(t < 0 ? -t : t);
+}
+__device__ __forceinline__ int dev_sgn(long long v) { return v > 0 ? 1 : (v == 0 ? 0 : -1); }
+
+__device__ __forceinline__ long long dev_mag(long long a, long long b) {  // rss()
+  long long c = dev_abs_trunc(a), d = dev_abs_trunc(b);
+  if (c == 0 && d == 0) return 0;
+  return (c > d) ? (d >> 1) + c : (c >> 1) + d;
+}
+
+__device__ __noinline__ unsigned dev_isqrt(long long L) {  // sqrt_newton()
+  long long t, div;
+  unsigned r = (unsigned)L;
+  if (L <= 0) return 0;
+  if (L & 0xFFFF0000LL)
+    div = (L & 0xFF000000LL) ? 0x3FFF : 0x3FF;
+  else
+    div = (L & 0x0FF00LL) ? 0x3F : ((L > 4) ? 0x7 : L);
+  for (;;) {
+    t = L / div + div;
+    div = t >> 1;
+    div += t & 1;
+    if ((long long)r > div)
+      r = (unsigned)div;
+    else {
+      if (1 / r == r - 1 && 1 % r == 0) r--;
+      return r;
+    }
+  }
+}
+
+__device__ __noinline__ long long dev_atan2(long long y, long long x) {  // fix_atan2(), 1 rad = 16384
+  const long long half_pi = 25736, pi = 51472;
+  long long n, n3, res = 0;
+  if (x == 0 && y == 0) return 0;
+  if (x > 0 && x >= dev_abs_trunc(y)) {
+    n = (y << 14) / x;
+    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    res = n - n3;
+  } else if (x <= 0 && -x >= dev_abs_trunc(y)) {
+    n = (y << 14) / x;
+    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    res = (y > 0) ? n - n3 + pi : n - n3 - pi;
+  } else if (y > 0 && y > dev_abs_trunc(x)) {
+    n = (x << 14) / y;
+    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    res = half_pi - n + n3;
+  } else if (y < 0 && -y > dev_abs_trunc(x)) {
+    n = (x << 14) / y;
+    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    res = -n + n3 - half_pi;
+  }
+  return res;
+}
+
+// indices into gnssb200_chan.accum[]
+#define A_IP 0
+#define A_QP 1
+#define A_IL 2
+#define A_QL 3
+#define A_IE 4
+#define A_QE 5
+
+__device__ __forceinline__ void dev_isr_search(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+  if (abs(k.n_freq) <= k.search_max_f) {
+    long long pm = dev_mag(k.accum[A_IP], k.accum[A_QP]);
+    if (pm > c.acq_thresh) {
+      k.state = 2;
+      k.i_confirm = 0;
+      k.n_thresh = 0;
+      k.mean_early = k.mean_prompt = k.mean_late = 0;
+    } else {
+      r.w_slew = reg16(1);
+      k.codes += 1;
+    }
+    if (k.codes == k.search_max_PRN_delay) {
+      k.n_freq += k.del_freq;
+      k.del_freq = -(k.del_freq + dev_sgn(k.del_freq));
+      k.carrier_freq = c.gps_carrier_ref + k.carrier_cold_corr + c.d_freq * k.n_freq;
+      dev_ch_carrier(r, c, k.carrier_freq);
+      k.codes = 0;
+    }
+  } else {
+    k.n_freq = 0;
+    k.del_freq = 1;
+    k.carrier_freq = c.gps_carrier_ref + k.carrier_cold_corr + c.d_freq * k.n_freq;
+    dev_ch_carrier(r, c, k.carrier_freq);
+    k.codes = 0;
+  }
+  k.CN0 = 0;
+}
+
+__device__ __forceinline__ void dev_isr_confirm(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+  long long pm = dev_mag(k.accum[A_IP], k.accum[A_QP]);
+  long long lm = dev_mag(k.accum[A_IL], k.accum[A_QL]);
+  long long em = dev_mag(k.accum[A_IE], k.accum[A_QE]);
+  k.mean_early += em;
+  k.mean_prompt += pm;
+  k.mean_late += lm;
+  if (pm > c.acq_thresh) k.n_thresh++;
+  if (k.i_confirm == 3) {          // CONFIRM_M
+    if (k.n_thresh >= 2) {         // N_OF_M_THRESH
+      k.state = 3;
+      k.CN0 = 0;
+      k.ch_time = 0;
+      k.ms_set = 0;
+      k.oldCarrNco = k.oldCodeNco = k.oldCarrError = k.oldCodeError = 0;
+      k.codeFreqBasis = c.gps_code_ref;
+      k.carrFreqBasis = k.carrier_freq;
+      k.sign_pos = k.prev_sign_pos = 0;
+    } else
+      k.state = 1;
+  }
+  k.i_confirm++;
+}
+
+__device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+  const int ip = k.accum[A_IP], qp = k.accum[A_QP], pip = k.prev_accum[A_IP], pqp = k.prev_accum[A_QP];
+  const int ie = k.accum[A_IE], qe = k.accum[A_QE], il = k.accum[A_IL], ql = k.accum[A_QL];
+  if (ip != 0 && qp != 0 && pip != 0 && pqp != 0) {
+    k.cross = (long long)(ip * pqp - pip * qp);  // int products, as in the reference
+    long long dt = (long long)(ip * pip + qp * pqp);
+    k.dot = dt < 0 ? -dt : dt;
+    k.cross >>= 8;
+    k.dot >>= 8;
+    k.freqError = dev_atan2(k.cross, k.dot);
+    long long aip = ip < 0 ? -(long long)ip : (long long)ip;
+    k.carrError = dev_atan2((long long)(qp * dev_sgn(ip)), aip) / 2;
+  } else {
+    k.freqError = 0;
+    k.carrError = k.oldCarrError;
+  }
+  k.carrNco = k.oldCarrNco + (c.pll_i1 * k.carrError - c.pll_i2 * k.oldCarrError - c.pll_i3 * k.freqError) / 51472;
+  k.oldCarrNco = k.carrNco;
+  k.oldCarrError = k.carrError;
+  k.carrFreq = k.carrFreqBasis + k.carrNco;
+  dev_ch_carrier(r, c, k.carrFreq);
+
+  if (ie != 0 && qe != 0 && il != 0 && ql != 0) {
+    unsigned se = dev_isqrt((long long)(ie * ie + qe * qe)), sl = dev_isqrt((long long)(il * il + ql * ql));
+    long long e = (long long)se;
+    e = e - (long long)sl;
+    e = 8192 * e;
+    e = e / (long long)((int)se + (int)sl);
+    k.codeError = e;
+  } else
+    k.codeError = k.oldCodeError;
+  k.codeNco = k.oldCodeNco + (((c.dll_i1 + 1) * k.codeError - c.dll_i2 * k.oldCodeError) / 8192);
+  k.oldCodeNco = k.codeNco;
+  k.oldCodeError = k.codeError;
+  k.codeFreq = k.codeFreqBasis - k.codeNco;
+  dev_ch_code(r, c, k.codeFreq);
+}
+
+__device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+  const int ip = k.accum[A_IP], pip = k.prev_accum[A_IP];
+  dev_isr_loops(k, r, c);
+  if (dev_sgn(ip) == -dev_sgn(pip)) {
+    k.prev_sign_pos = k.sign_pos;
+    k.sign_pos = (int)k.ch_time;
+    if (k.sign_pos - k.prev_sign_pos > 19)
+      k.sign_count++;
+    else
+      k.sign_count = 0;
+  }
+  k.ms_count++;
+  if ((dev_sgn(ip) == -1 && (k.ms_sign & 0xfffffULL) == 0x00000ULL) ||
+      (dev_sgn(ip) == 1 && (k.ms_sign & 0xfffffULL) == 0xfffffULL)) {
+    if (dev_sgn(ip) == -dev_sgn(pip)) {
+      k.ms_count = 0;
+      r.w_epoch = reg16(0x1);
+      k.ms_set = 1;
+    }
+  }
+  k.ms_sign <<= 1;
+  if (ip < 0) k.ms_sign |= 1;
+  k.ms_count %= 20;
+  k.ch_time++;
+  if (k.sign_count > 30 && k.ms_set) k.state = 4;
+  if (k.ch_time == 3000) {
+    k.del_freq = 1;
+    k.n_freq = 0;
+    dev_ch_carrier(r, c, c.gps_carrier_ref);
+    dev_ch_code(r, c, c.gps_code_ref);
+    k.codes = 0;
+    k.ch_time = 0;
+    k.state = 1;
+  }
+}
+
+__device__ __forceinline__ void dev_isr_track(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+  dev_isr_loops(k, r, c);
+  k.ms_count = (k.ms_count + 1) % 20;
+  if (k.ms_count == 19) k.bit = k.accum[A_IP] > 0 ? 1 : 0;
+}
+
+// One channel's share of gpsisr() for a block in which it dumped.  Returns 1 on CHANNEL_OFF (the
+// reference exit(0)s there).
+__device__ __forceinline__ int dev_gpsisr_channel(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+#pragma unroll
+  for (int a = 0; a < 6; a++) k.prev_accum[a] = k.accum[a];
+  k.accum[A_IE] = (int16_t)r.r_acc[4];  // from_gps(): short
+  k.accum[A_QE] = (int16_t)r.r_acc[5];
+  k.accum[A_IP] = (int16_t)r.r_acc[2];
+  k.accum[A_QP] = (int16_t)r.r_acc[3];
+  k.accum[A_IL] = (int16_t)r.r_acc[0];
+  k.accum[A_QL] = (int16_t)r.r_acc[1];
+  switch (k.state) {
+    case 0: return 1;
+    case 1: dev_isr_search(k, r, c); break;
+    case 2: dev_isr_confirm(k, r, c); break;
+    case 3: dev_isr_pull_in(k, r, c); break;
+    case 4: dev_isr_track(k, r, c); break;
+    default: break;
+  }
+  return 0;
+}

@@ -1,0 +1,695 @@
+// track.cu -- GP2021-style E/P/L correlator bank + closed channel loop on the device.
+//
+// What it replaces: Sim_GP2021_int (OSG/correlator/correlator.c:148-316) followed by gpsisr
+// (OSG/isr/osgpsisr.c:360-408) once per 512 us block, for S independent IF streams x 12 channels.
+//
+// Mapping (B200): one CTA per (stream, channel).  Channels of a receiver never exchange data in
+// the reference (each dump only touches its own registers and its own struct tracking_channel), so
+// a CTA runs its channel through all blocks without any grid-wide synchronisation:
+//
+//   per block:  every thread takes SPT consecutive complex samples (16-byte vector loads, next
+//               block prefetched into registers), starts its carrier/code NCOs from the closed form
+//               phase(i) = phase0 + i*incr, and walks its samples with the
+//               exact integer arithmetic of the reference: 8-phase LO (phase>>29), complex mix,
+//               +-1 E/P/L code taps at half-chip spacing, code-NCO carry -> next half chip.
+//               I and Q products ride in one 32-bit register as two 16-bit lanes (|sum| <= 32*384
+//               per thread), so the six MACs of the reference are three IMADs.
+//   dump:       at most one per block on this path; a chunk lies before, after or across it.  The
+//               (single) straddling chunk is re-evaluated sample-per-lane by its warp with the
+//               closed forms, so no thread carries two accumulator sets through its loop.
+//   reduce:     __reduce_add_sync (REDUX) per warp, 12 partials per warp through shared memory.
+//   ISR:        lane 0 of warp 0 applies the dump / TIC / epoch rules, runs the channel state
+//               machine (isr_device.cuh) and publishes next block's NCO words.
+//
+// Register values the fast path cannot express (a second dump inside one block, half-chip counts
+// beyond two table rows, PRN outside 1..32, ...) take the serial path: lane 0 walks the block
+// with the literal per-sample loop.  It is still device code; there is no CPU fallback.
+#include "isr_device.cuh"
+
+#define MODE_STOP (-1)
+#define MODE_IDLE 0
+#define MODE_FAST 1
+#define MODE_SERIAL 2
+
+#define SMEM_TBL 4096  // two table rows (prn, prn+1) + 4
+
+struct StepParams {
+  uint32_t cph0, kph0, cinc, kinc;
+  uint32_t hc0, w1, stale_idx, slew_dump;
+  int mode;
+  int tic_count;
+};
+
+struct TrackArgs {
+  gnssb200_rx *rx;
+  int32_t *chan_flags;
+  const uint32_t *code_table;
+  const uint8_t *d_if;
+  size_t stride;
+  int fmt, nsamp;
+  long long nblocks;
+  int run_isr;
+  int first_stream;
+  gnssb200_dump *dumps;
+  int dump_cap;
+  int32_t *dump_count;
+  gnssb200_cfg cfg;
+};
+
+// byte k of w, sign extended, in one PRMT: selector nibble k copies the byte, nibble k|8 replicates
+// its sign bit (PTX prmt default mode).  Inline PTX because __byte_perm() documents only 3 selector bits.
+__device__ __forceinline__ int sext8(uint32_t w, int k) {
+  const uint32_t sel = 0x8880u | (uint32_t)(k * 0x1111);
+  int r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"(sel));
+  return r;
+}
+
+// 8-phase LO of the GP2021 / Namuru carrier NCO (correlator.c:203-204, NAM/rtl/carrier_nco.v:21-25),
+// stored so that  I*lut.x + Q*lut.y = ival + 65536*qval  with
+//   ival = i_lo*I + q_lo*Q,  qval = q_lo*I - i_lo*Q   (correlator.c:214-215)
+__device__ __forceinline__ void fill_lo_lut(uint2 *lut) {
+  const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
+  const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
+  if (threadIdx.x < 8) {
+    int k = threadIdx.x;
+    lut[k].x = (uint32_t)(i_lo[k] + 65536 * q_lo[k]);
+    lut[k].y = (uint32_t)(q_lo[k] - 65536 * i_lo[k]);
+  }
+}
+
+__device__ __forceinline__ size_t bytes_for(int fmt, long long nsamples) {
+  return fmt == GNSSB200_FMT_INT8_IQ ? (size_t)nsamples * 2 : (fmt == GNSSB200_FMT_PACKED2 ? (size_t)nsamples / 2 : (size_t)nsamples);
+}
+
+// one complex sample from a block, any format (slow, used by the serial path, tails, straddle fix-up)
+__device__ __forceinline__ void load_sample(const uint8_t *blk, int fmt, int i, int &I, int &Q) {
+  if (fmt == GNSSB200_FMT_INT8_IQ) {
+    const int8_t *p = (const int8_t *)blk + 2 * (size_t)i;
+    I = p[0];
+    Q = p[1];
+  } else if (fmt == GNSSB200_FMT_PACKED2) {
+    uint32_t b = blk[i >> 1] >> ((i & 1) * 4);
+    const int val[4] = {1, -1, 3, -3};  // FE/.../win32_sampler.h:45-55
+    I = val[b & 3];
+    Q = val[(b >> 2) & 3];
+  } else {
+    I = ((const int8_t *)blk)[i];
+    Q = 0;
+  }
+}
+
+// SPT consecutive samples starting at i0 -> SPT/2 words of (I0,Q0,I1,Q1) int8
+template <int SPT>
+__device__ __forceinline__ void load_chunk(const uint8_t *blk, int fmt, int i0, int nsamp, bool aligned,
+                                           const uint32_t *unpack_lut, uint32_t (&w)[SPT / 2]) {
+  if (i0 + SPT <= nsamp && aligned) {
+    if (fmt == GNSSB200_FMT_INT8_IQ) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(blk + 2 * (size_t)i0);
+#pragma unroll
+      for (int q = 0; q < SPT / 8; q++) {
+        uint4 v = __ldg(p + q);
+        w[4 * q + 0] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+      }
+    } else if (fmt == GNSSB200_FMT_PACKED2) {
+      // SPT/2 bytes; each byte -> one word through the 256-entry shared LUT
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(blk + (size_t)(i0 >> 1));
+#pragma unroll
+      for (int q = 0; q < SPT / 8; q++) {
+        uint32_t v = __ldg(p + q);
+        w[4 * q + 0] = unpack_lut[v & 0xff];
+        w[4 * q + 1] = unpack_lut[(v >> 8) & 0xff];
+        w[4 * q + 2] = unpack_lut[(v >> 16) & 0xff];
+        w[4 * q + 3] = unpack_lut[v >> 24];
+      }
+    } else {
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(blk + (size_t)i0);
+#pragma unroll
+      for (int q = 0; q < SPT / 4; q++) {
+        uint32_t v = __ldg(p + q);
+        w[2 * q + 0] = __byte_perm(v, 0, 0x4140);  // (I0,0,I1,0)
+        w[2 * q + 1] = __byte_perm(v, 0, 0x4342);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < SPT / 2; q++) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int i = i0 + 2 * q + e;
+        if (i < nsamp) {
+          int I, Q;
+          load_sample(blk, fmt, i, I, Q);
+          word |= ((uint32_t)(I & 0xff) | ((uint32_t)(Q & 0xff) << 8)) << (16 * e);
+        }
+      }
+      w[q] = word;
+    }
+  }
+}
+
+// The per-thread hot loop: SPT samples, running NCOs, packed I/Q MACs.
+template <int SPT>
+__device__ __forceinline__ void correlate_chunk(const uint32_t (&w)[SPT / 2], uint32_t cph, uint32_t kph,
+                                                const uint32_t cinc, const uint32_t kinc, const uint32_t *tbl,
+                                                uint32_t h, uint32_t bits, const uint2 *lut, int &accE, int &accP,
+                                                int &accL) {
+  int cE = sext8(bits, 0), cP = sext8(bits, 1), cL = sext8(bits, 2);
+  int aE = 0, aP = 0, aL = 0;
+#pragma unroll
+  for (int j = 0; j < SPT; j++) {
+    const uint32_t word = w[j >> 1];
+    const int I = sext8(word, (j & 1) * 2), Q = sext8(word, (j & 1) * 2 + 1);
+    const uint2 ab = lut[cph >> 29];
+    const int v = I * (int)ab.x + Q * (int)ab.y;  // ival + 65536*qval
+    aE += cE * v;
+    aP += cP * v;
+    aL += cL * v;
+    cph += cinc;
+    const uint32_t k2 = kph + kinc;
+    if (k2 < kph) {  // code NCO carry: next half chip (correlator.c:246-250)
+      h++;
+      const uint32_t t = tbl[h];
+      cE = sext8(t, 0);
+      cP = sext8(t, 1);
+      cL = sext8(t, 2);
+    }
+    kph = k2;
+  }
+  accE = aE;
+  accP = aP;
+  accL = aL;
+}
+
+__device__ __forceinline__ void unpack_lanes(int packed, int &lo, int &hi) {
+  lo = (int)(short)(packed & 0xffff);
+  hi = (packed - lo) >> 16;
+}
+
+// ---- lane-0 bookkeeping -----------------------------------------------------------------------
+struct ChanShared {
+  gnssb200_chan k;
+  gnssb200_corr g;
+  ChRegs r;
+  long long tic;
+  int dumped_last;
+  int halted;
+  int dump_count;
+};
+
+__device__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+  const long long n = a.nsamp;
+  if (cs.tic < n) {  // correlator.c:155-165
+    sp.tic_count = (int)cs.tic;
+    cs.tic += a.cfg.tic_ref - n;
+  } else {
+    cs.tic -= n;
+    sp.tic_count = -1;
+  }
+  ChRegs &r = cs.r;
+  gnssb200_corr &g = cs.g;
+  if (r.w_epoch != -1) {  // :177-182
+    r.r_meas[7] = r.w_epoch;
+    g.ms_counter = r.w_epoch & 0xff;
+    g.bit_counter = r.w_epoch >> 8;
+    r.w_epoch = -1;
+  }
+  if (r.w_prn <= 0) {
+    sp.mode = MODE_IDLE;
+    return;
+  }
+  sp.cinc = (uint32_t)((r.w_carr_hi << 16) + r.w_carr_lo);
+  sp.kinc = (uint32_t)((r.w_code_hi << 16) + r.w_code_lo) << 1;
+  sp.cph0 = g.carrier_phase;
+  sp.kph0 = g.code_phase;
+  sp.hc0 = g.half_chip & 0xffff;
+  const long long slew_dump = (long long)r.w_slew + HALF_CHIPS;  // :172
+  sp.slew_dump = (uint32_t)slew_dump;
+  const long long w1 = ((long long)sp.hc0 + 1 >= slew_dump) ? 1 : slew_dump - sp.hc0;
+  const unsigned long long wtot = ((unsigned long long)sp.kph0 + (unsigned long long)n * sp.kinc) >> 32;
+  sp.w1 = (uint32_t)w1;
+  sp.stale_idx = (uint32_t)(sp.hc0 + w1);
+  bool fast = (r.w_prn == tbl_prn) && r.w_prn >= 1 && r.w_prn <= 32 && slew_dump >= 1 && slew_dump < 65536 &&
+              (long long)wtot < w1 + slew_dump && (sp.hc0 + wtot + 40) < SMEM_TBL && (sp.hc0 + w1) < SMEM_TBL &&
+              n < (1ll << 30);
+  sp.mode = fast ? MODE_FAST : MODE_SERIAL;
+}
+
+// dump side effects common to both paths (correlator.c:252-281)
+__device__ __forceinline__ void apply_dump_counters(ChanShared &cs) {
+  gnssb200_corr &g = cs.g;
+  cs.r.w_slew = 0;
+  g.ms_counter++;
+  if (g.ms_counter == 20) g.bit_counter = (g.bit_counter + 1) % 50;
+  g.ms_counter %= 20;
+  cs.r.r_meas[7] = g.ms_counter + (g.bit_counter << 8);
+}
+
+__device__ void finalize_fast(ChanShared &cs, const StepParams &sp, const int (&A)[6], const int (&B)[6], int nsamp) {
+  gnssb200_corr &g = cs.g;
+  ChRegs &r = cs.r;
+  const unsigned long long n = (unsigned long long)nsamp;
+  const unsigned long long kend = (unsigned long long)sp.kph0 + n * sp.kinc;
+  const unsigned long long cend = (unsigned long long)sp.cph0 + n * sp.cinc;
+  const uint32_t wtot = (uint32_t)(kend >> 32);
+  const bool dumped = sp.w1 <= wtot;
+  const int epoch_before = r.r_meas[7];
+  if (dumped) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      r.r_acc[q] = g.acc[q] + A[q];
+      g.acc[q] = B[q];
+    }
+    apply_dump_counters(cs);
+    g.half_chip = wtot - sp.w1;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 6; q++) g.acc[q] += A[q] + B[q];
+    g.half_chip = sp.hc0 + wtot;
+  }
+  cs.dumped_last = dumped ? 1 : 0;
+  const uint32_t ctot = (uint32_t)(cend >> 32);
+  if (sp.tic_count >= 0 && sp.tic_count < nsamp) {  // measurement latch, :286-303
+    const unsigned long long m = (unsigned long long)sp.tic_count + 1;
+    const unsigned long long kt = (unsigned long long)sp.kph0 + m * sp.kinc;
+    const unsigned long long ct = (unsigned long long)sp.cph0 + m * sp.cinc;
+    const uint32_t wa = (uint32_t)(kt >> 32), cw = (uint32_t)(ct >> 32);
+    const bool by_tic = dumped && sp.w1 <= wa;
+    r.r_meas[4] = by_tic ? r.r_meas[7] : epoch_before;
+    r.r_meas[3] = (int)((uint32_t)ct >> 22);
+    r.r_meas[1] = (int)(by_tic ? wa - sp.w1 : sp.hc0 + wa);
+    r.r_meas[5] = (int)((uint32_t)kt >> 22);
+    const uint32_t cyc = g.carrier_cycle + cw;
+    r.r_meas[2] = (int)(cyc & 0xffff);
+    r.r_meas[6] = (int)(cyc >> 16);
+    g.carrier_cycle = ctot - cw;
+  } else {
+    g.carrier_cycle += ctot;
+  }
+  g.carrier_phase = (uint32_t)cend;
+  g.code_phase = (uint32_t)kend;
+}
+
+// literal per-sample walk of one block by a single lane (any register contents)
+__device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, const TrackArgs &a, const uint8_t *blk) {
+  const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
+  const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
+  gnssb200_corr &g = cs.g;
+  ChRegs &r = cs.r;
+  const long long row = (long long)r.w_prn * HALF_CHIPS;
+  const int dump_at = r.w_slew + HALF_CHIPS;
+  uint16_t hc = (uint16_t)g.half_chip;
+  auto bits_at = [&](uint16_t hh) -> uint32_t {
+    long long f = row + hh;
+    return (f >= 0 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+  };
+  uint32_t t = bits_at(hc);
+  int cE = sext8(t, 0), cP = sext8(t, 1), cL = sext8(t, 2);
+  int dumped = 0;
+  for (int i = 0; i < a.nsamp; i++) {
+    const int k = g.carrier_phase >> 29;
+    int I, Q;
+    load_sample(blk, a.fmt, i, I, Q);
+    const int vq = q_lo[k] * I - i_lo[k] * Q;
+    const int vi = i_lo[k] * I + q_lo[k] * Q;
+    g.acc[0] += cL * vi;
+    g.acc[1] += cL * vq;
+    g.acc[2] += cP * vi;
+    g.acc[3] += cP * vq;
+    g.acc[4] += cE * vi;
+    g.acc[5] += cE * vq;
+    uint32_t before = g.carrier_phase;
+    g.carrier_phase += sp.cinc;
+    if (g.carrier_phase < before) g.carrier_cycle++;
+    before = g.code_phase;
+    g.code_phase += sp.kinc;
+    if (g.code_phase < before) {
+      hc++;
+      t = bits_at(hc);
+      cE = sext8(t, 0);
+      cP = sext8(t, 1);
+      cL = sext8(t, 2);
+      if (hc >= dump_at) {
+        for (int q = 0; q < 6; q++) {
+          r.r_acc[q] = g.acc[q];
+          g.acc[q] = 0;
+        }
+        apply_dump_counters(cs);
+        hc = 0;
+        dumped = 1;
+      }
+    }
+    if (i == sp.tic_count) {
+      r.r_meas[4] = r.r_meas[7];
+      r.r_meas[3] = (int)(g.carrier_phase >> 22);
+      r.r_meas[1] = hc;
+      r.r_meas[5] = (int)(g.code_phase >> 22);
+      r.r_meas[2] = (int)(g.carrier_cycle & 0xffff);
+      r.r_meas[6] = (int)(g.carrier_cycle >> 16);
+      g.carrier_cycle = 0;
+    }
+  }
+  g.half_chip = hc;
+  cs.dumped_last = dumped;
+}
+
+__device__ void after_block(ChanShared &cs, const TrackArgs &a, int s, int ch, long long block_index) {
+  if (!cs.dumped_last) return;
+  if (a.run_isr) {
+    if (dev_gpsisr_channel(cs.k, cs.r, a.cfg)) {
+      cs.halted = 1;
+      return;
+    }
+  }
+  if (a.dumps && cs.dump_count < a.dump_cap) {
+    gnssb200_dump d;
+    d.block = (int32_t)block_index;
+    d.ch = (int16_t)ch;
+    d.state = (int16_t)cs.k.state;
+#pragma unroll
+    for (int q = 0; q < 6; q++) d.acc[q] = cs.r.r_acc[q];
+    d.carrier_incr = (uint32_t)((cs.r.w_carr_hi << 16) + cs.r.w_carr_lo);
+    d.code_incr = (uint32_t)((cs.r.w_code_hi << 16) + cs.r.w_code_lo);
+    d.n_freq = (int16_t)cs.k.n_freq;
+    d.codes = (int16_t)cs.k.codes;
+    d.slew = cs.r.w_slew;
+    a.dumps[((size_t)s * NCH + ch) * a.dump_cap + cs.dump_count] = d;
+    cs.dump_count++;
+  }
+}
+
+template <int SPT>
+__global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const TrackArgs a) {
+  __shared__ ChanShared cs;
+  __shared__ StepParams sp_s;
+  __shared__ uint2 lut[8];
+  __shared__ uint32_t tbl[SMEM_TBL];
+  __shared__ uint32_t unpack_lut[256];
+  __shared__ int partial[32][12];
+
+  const int s = a.first_stream + blockIdx.x / NCH, ch = blockIdx.x % NCH;
+  gnssb200_rx *rx = a.rx + s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tbl_prn = rx->reg_write[ch << 3];
+
+  fill_lo_lut(lut);
+  for (int i = tid; i < SMEM_TBL; i += blockDim.x) {
+    long long f = (long long)tbl_prn * HALF_CHIPS + i;
+    tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+  }
+  for (int i = tid; i < 256; i += blockDim.x) {
+    const int val[4] = {1, -1, 3, -3};
+    uint32_t wv = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) wv |= (uint32_t)(val[(i >> (2 * e)) & 3] & 0xff) << (8 * e);
+    unpack_lut[i] = wv;
+  }
+  if (tid == 0) {
+    cs.k = rx->chan[ch];
+    cs.g = rx->corr[ch];
+    const int b8 = ch << 3;
+    cs.r.w_prn = rx->reg_write[b8];
+    cs.r.w_carr_hi = rx->reg_write[b8 + 3];
+    cs.r.w_carr_lo = rx->reg_write[b8 + 4];
+    cs.r.w_code_hi = rx->reg_write[b8 + 5];
+    cs.r.w_code_lo = rx->reg_write[b8 + 6];
+    cs.r.w_epoch = rx->reg_write[b8 + 7];
+    cs.r.w_slew = rx->reg_write[b8 + 0x84];
+    for (int q = 0; q < 8; q++) cs.r.r_meas[q] = rx->reg_read[b8 + q];
+    for (int q = 0; q < 6; q++) cs.r.r_acc[q] = rx->reg_read[b8 + 0x84 + q];
+    cs.tic = rx->tic;
+    cs.dumped_last = 0;
+    cs.halted = 0;
+    cs.dump_count = a.dump_count ? a.dump_count[s * NCH + ch] : 0;
+    if (a.nblocks > 0 && !rx->halted)
+      prepare_block(cs, sp_s, a, tbl_prn);
+    else
+      sp_s.mode = MODE_STOP;
+  }
+  __syncthreads();
+
+  const size_t blk_bytes = bytes_for(a.fmt, a.nsamp);
+  const uint8_t *stream_base = a.d_if + (size_t)s * a.stride;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(stream_base) | blk_bytes) & 15) == 0 && (a.nsamp % 8) == 0;
+  const long long first_block = rx->blocks_done;
+
+  uint32_t cur[SPT / 2], nxt[SPT / 2];
+  const int my_i0 = tid * SPT;
+  if (sp_s.mode != MODE_STOP && my_i0 < a.nsamp) load_chunk<SPT>(stream_base, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, cur);
+
+  for (long long b = 0; b < a.nblocks; b++) {
+    const StepParams sp = sp_s;
+    if (sp.mode == MODE_STOP) break;
+    const uint8_t *blk = stream_base + (size_t)b * blk_bytes;
+    int sumA[6] = {0, 0, 0, 0, 0, 0}, sumB[6] = {0, 0, 0, 0, 0, 0};
+    bool anyB = false;
+
+    if (sp.mode == MODE_FAST) {
+      // trip count is uniform over the CTA (warp collectives inside); `live` masks ragged tails
+      for (int base = 0, tile = 0; base < a.nsamp; base += blockDim.x * SPT, tile++) {
+        const int i0 = base + my_i0;
+        const bool live = i0 < a.nsamp;
+        if (tile > 0 && live) load_chunk<SPT>(blk, a.fmt, i0, a.nsamp, aligned, unpack_lut, cur);
+        const int i1 = live ? min(i0 + SPT, a.nsamp) : i0 + 1;
+        const unsigned long long k0 = (unsigned long long)sp.kph0 + (unsigned long long)i0 * sp.kinc;
+        const uint32_t w_start = (uint32_t)(k0 >> 32);
+        const uint32_t w_lastb = (uint32_t)(((unsigned long long)sp.kph0 + (unsigned long long)(i1 - 1) * sp.kinc) >> 32);
+        const bool allA = !live || w_lastb < sp.w1, allB = live && w_start >= sp.w1;
+        uint32_t h, hl;
+        if (allB) {
+          h = w_start - sp.w1;
+          hl = (h == 0) ? sp.stale_idx : h;  // stale bits after the dump (SURVEY.md App. A rule A6)
+        } else {
+          h = sp.hc0 + w_start;
+          hl = h;
+        }
+        int pE = 0, pP = 0, pL = 0;
+        if (live)
+          correlate_chunk<SPT>(cur, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc, tbl, h, tbl[hl],
+                               lut, pE, pP, pL);
+        const bool straddle = !allA && !allB;
+        if (!straddle && live) {
+          int v[6];
+          unpack_lanes(pL, v[0], v[1]);
+          unpack_lanes(pP, v[2], v[3]);
+          unpack_lanes(pE, v[4], v[5]);
+          if (allA) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) sumA[q] += v[q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 6; q++) sumB[q] += v[q];
+          }
+        }
+        // the chunk that contains the dump is re-evaluated one sample per lane by its warp
+        unsigned m = __ballot_sync(0xffffffffu, straddle);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int si0 = __shfl_sync(0xffffffffu, i0, src);
+          for (int i = si0 + lane; i < min(si0 + SPT, a.nsamp); i += 32) {
+            const unsigned long long ki = (unsigned long long)sp.kph0 + (unsigned long long)i * sp.kinc;
+            const uint32_t wb = (uint32_t)(ki >> 32);
+            const bool inA = wb < sp.w1;
+            const uint32_t rel = wb - sp.w1;
+            const uint32_t hh = inA ? sp.hc0 + wb : (rel == 0 ? sp.stale_idx : rel);
+            const uint32_t t = tbl[hh];
+            int I, Q;
+            load_sample(blk, a.fmt, i, I, Q);
+            const uint2 ab = lut[(sp.cph0 + (uint32_t)i * sp.cinc) >> 29];
+            const int v = I * (int)ab.x + Q * (int)ab.y;
+            int vi, vq;
+            unpack_lanes(v, vi, vq);
+            const int cE = sext8(t, 0), cP = sext8(t, 1), cL = sext8(t, 2);
+            if (inA) {
+              sumA[0] += cL * vi; sumA[1] += cL * vq; sumA[2] += cP * vi;
+              sumA[3] += cP * vq; sumA[4] += cE * vi; sumA[5] += cE * vq;
+            } else {
+              sumB[0] += cL * vi; sumB[1] += cL * vq; sumB[2] += cP * vi;
+              sumB[3] += cP * vq; sumB[4] += cE * vi; sumB[5] += cE * vq;
+            }
+          }
+        }
+        anyB |= !allA;
+      }
+#ifdef TRACK_DEBUG
+      if (ch == 0 && b < 2 && (tid < 3 || tid == 255))
+        printf("  tid=%d b=%lld sumA=%d %d %d %d %d %d cur0=%08x\n", tid, b, sumA[0], sumA[1], sumA[2], sumA[3], sumA[4], sumA[5], cur[0]);
+#endif
+      // prefetch this thread's first chunk of the next block while the reduction / ISR runs
+      if (b + 1 < a.nblocks && my_i0 < a.nsamp)
+        load_chunk<SPT>(blk + blk_bytes, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, nxt);
+      // warp reduction
+      const bool warpB = __any_sync(0xffffffffu, anyB);
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        int ra = __reduce_add_sync(0xffffffffu, sumA[q]);
+        int rb = warpB ? __reduce_add_sync(0xffffffffu, sumB[q]) : 0;
+        if (lane == 0) {
+          partial[warp][q] = ra;
+          partial[warp][6 + q] = rb;
+        }
+      }
+    } else if (b + 1 < a.nblocks && my_i0 < a.nsamp) {
+      load_chunk<SPT>(blk + blk_bytes, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, nxt);
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+      int A[6], B[6];
+      if (sp.mode == MODE_FAST) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          A[q] = __reduce_add_sync(0xffffffffu, lane < nwarps ? partial[lane][q] : 0);
+          B[q] = __reduce_add_sync(0xffffffffu, lane < nwarps ? partial[lane][6 + q] : 0);
+        }
+      }
+      if (tid == 0) {
+#ifdef TRACK_DEBUG
+        if (ch == 0 && b < 4)
+          printf("b=%lld mode=%d cph0=%u kph0=%u cinc=%u kinc=%u hc0=%u w1=%u stale=%u A=%d %d %d %d %d %d B=%d %d %d %d %d %d\n", b,
+                 sp.mode, sp.cph0, sp.kph0, sp.cinc, sp.kinc, sp.hc0, sp.w1, sp.stale_idx, A[0], A[1], A[2], A[3], A[4], A[5],
+                 B[0], B[1], B[2], B[3], B[4], B[5]);
+#endif
+        if (sp.mode == MODE_FAST)
+          finalize_fast(cs, sp, A, B, a.nsamp);
+        else if (sp.mode == MODE_SERIAL)
+          serial_block(cs, sp, a, blk);
+        else
+          cs.dumped_last = 0;
+        after_block(cs, a, s, ch, first_block + b);
+        if (cs.halted || sp.mode == MODE_IDLE)  // an idle channel has no ISR: nothing can change any more
+          sp_s.mode = MODE_STOP;
+        else if (b + 1 < a.nblocks)
+          prepare_block(cs, sp_s, a, tbl_prn);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SPT / 2; q++) cur[q] = nxt[q];
+  }
+
+  if (tid == 0) {
+    rx->chan[ch] = cs.k;
+    rx->corr[ch] = cs.g;
+    const int b8 = ch << 3;
+    rx->reg_write[b8 + 3] = cs.r.w_carr_hi;
+    rx->reg_write[b8 + 4] = cs.r.w_carr_lo;
+    rx->reg_write[b8 + 5] = cs.r.w_code_hi;
+    rx->reg_write[b8 + 6] = cs.r.w_code_lo;
+    rx->reg_write[b8 + 7] = cs.r.w_epoch;
+    rx->reg_write[b8 + 0x84] = cs.r.w_slew;
+    for (int q = 1; q < 8; q++) rx->reg_read[b8 + q] = cs.r.r_meas[q];
+    for (int q = 0; q < 6; q++) rx->reg_read[b8 + 0x84 + q] = cs.r.r_acc[q];
+    a.chan_flags[s * NCH + ch] = (cs.dumped_last ? 1 : 0) | (cs.halted ? 2 : 0);
+    if (a.dump_count) a.dump_count[s * NCH + ch] = cs.dump_count;
+  }
+}
+
+// one thread per stream: status words, TIC counter and block counter after a run
+__global__ void track_finish_kernel(gnssb200_rx *rx, const int32_t *chan_flags, int first_stream, int n_streams,
+                                    int nsamp, long long nblocks, long long tic_ref) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_streams) return;
+  const int s = first_stream + t;
+  gnssb200_rx *r = rx + s;
+  if (nblocks <= 0 || r->halted) return;
+  int status = 0, halted = 0;
+  for (int ch = 0; ch < NCH; ch++) {
+    const int f = chan_flags[s * NCH + ch];
+    if (f & 1) status |= 1 << ch;
+    if (f & 2) halted = 1;
+  }
+  long long tic = r->tic;
+  int tic_count = -1;
+  for (long long b = 0; b < nblocks; b++) {
+    if (tic < nsamp) {
+      tic_count = (int)tic;
+      tic += tic_ref - nsamp;
+    } else {
+      tic -= nsamp;
+      tic_count = -1;
+    }
+  }
+  r->tic = tic;
+  r->reg_read[0x82] = status;                        // correlator.c:309
+  r->reg_read[0x83] = (tic_count > -1) ? 0x2000 : 0; // :312-315
+  r->blocks_done += nblocks;
+  if (halted) r->halted = 1;
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+void build_code_table_host(uint32_t *table) {
+  // C/A Gold codes, G2 register start states per PRN (IS-GPS-200; same values as correlator.c:67-71),
+  // replicas at half-chip spacing: early[h]=c[h>>1], prompt[h]=c[((h+1)%2046)>>1], late[h]=c[((h+2)%2046)>>1]
+  static const int g2_start[33] = {0x000, 0x3f6, 0x3ec, 0x3d8, 0x3b0, 0x04b, 0x096, 0x2cb, 0x196, 0x32c, 0x3ba,
+                                   0x374, 0x1d0, 0x3a0, 0x340, 0x280, 0x100, 0x113, 0x226, 0x04c, 0x098, 0x130,
+                                   0x260, 0x267, 0x338, 0x270, 0x0e0, 0x1c0, 0x380, 0x22b, 0x056, 0x0ac, 0x158};
+  for (int i = 0; i <= TABLE_ENTRIES; i++) table[i] = 0;
+  for (int prn = 1; prn <= 32; prn++) {
+    int chip[1023];
+    int g1 = 0x1FF, g2 = g2_start[prn];
+    chip[0] = 1;
+    for (int c = 1; c < 1023; c++) {
+      chip[c] = (g1 ^ g2) & 1;
+      g1 = (g1 >> 1) | (((g1 << 2) ^ (g1 << 9)) & 0x200);
+      g2 = (g2 >> 1) | (((g2 << 1) ^ (g2 << 2) ^ (g2 << 5) ^ (g2 << 7) ^ (g2 << 8) ^ (g2 << 9)) & 0x200);
+    }
+    for (int h = 0; h < HALF_CHIPS; h++) {
+      const int e = 2 * chip[(h % HALF_CHIPS) >> 1] - 1;
+      const int p = 2 * chip[((h + 1) % HALF_CHIPS) >> 1] - 1;
+      const int l = 2 * chip[((h + 2) % HALF_CHIPS) >> 1] - 1;
+      table[prn * HALF_CHIPS + h] = (uint32_t)(e & 0xff) | ((uint32_t)(p & 0xff) << 8) | ((uint32_t)(l & 0xff) << 16);
+    }
+  }
+}
+
+int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void *d_if, size_t stride, int fmt,
+                 int nsamp, long long nblocks, int run_isr, gnssb200_dump *d_dumps, int dump_cap,
+                 int32_t *d_dump_count, cudaStream_t st) {
+  if (n_streams <= 0 || nblocks <= 0) return 0;
+  TrackArgs a;
+  a.rx = h->d_rx;
+  a.chan_flags = h->d_chan_flags;
+  a.code_table = h->d_code_table;
+  a.d_if = (const uint8_t *)d_if - (size_t)first_stream * stride;  // kernel indexes by absolute stream
+  a.stride = stride;
+  a.fmt = fmt;
+  a.nsamp = nsamp;
+  a.nblocks = nblocks;
+  a.run_isr = run_isr;
+  a.first_stream = first_stream;
+  a.dumps = d_dumps;
+  a.dump_cap = dump_cap;
+  a.dump_count = d_dump_count;
+  a.cfg = h->cfg;
+  const int grid = n_streams * NCH;
+  // threads: one tile of SPT-sample chunks covers the block when possible
+  static int forced_spt = -1;
+  if (forced_spt < 0) {
+    const char *e = getenv("GNSSB200_TRACK_SPT");
+    forced_spt = e ? atoi(e) : 0;
+  }
+  int spt = forced_spt ? forced_spt : 32;
+  int threads = (nsamp + spt - 1) / spt;
+  threads = ((threads + 31) / 32) * 32;
+  const int max_threads = 1024 / (spt / 8);
+  if (threads > max_threads) threads = max_threads;
+  if (threads < 32) threads = 32;
+  if (spt == 32)
+    track_loop_kernel<32><<<grid, threads, 0, st>>>(a);
+  else if (spt == 16)
+    track_loop_kernel<16><<<grid, threads, 0, st>>>(a);
+  else
+    track_loop_kernel<8><<<grid, threads, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  track_finish_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(h->d_rx, h->d_chan_flags, first_stream, n_streams, nsamp,
+                                                               nblocks, h->cfg.tic_ref);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  return 0;
+}

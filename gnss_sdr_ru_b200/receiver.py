@@ -1,0 +1,167 @@
+"""Host-side mirror of the reference receiver's correlator / channel interface, backed by the GPU.
+
+Names follow the reference (OSG/gp2021/gp2021.h:7-18, OSG/correlator/correlator.h:8-9,
+OSG/osgnss_next_step.c:41-84): ``ch_cntl``, ``ch_carrier``, ``ch_code``, ``ch_code_slew``,
+``ch_epoch_load``, ``simple_cold_allocate``, ``correlator_init``, ``Sim_GP2021_int``.
+
+* :class:`DropInCorrelator` -- the library's drop-in symbols exactly as the reference C host would
+  call them (one receiver, one block per call, host buffers).
+* :class:`TrackingEngine` -- the batched closed loop: S receivers x 12 channels resident on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .lib import GnssB200Error, check, default_cfg, lib
+
+NSAMP_DEFAULT = 8192  # SAMP_RATE*interr_int/1e6, OSG/osgnss_next_step.c:150
+
+
+class DropInCorrelator:
+    """correlator_init / Sim_GP2021_int / REG_read / REG_write of libgnssb200.so (process-global)."""
+
+    def __init__(self, tic_period: float = 0.0):
+        self.L = lib()
+        self.REG_read = (C.c_int * 256).in_dll(self.L, "REG_read")
+        self.REG_write = (C.c_int * 256).in_dll(self.L, "REG_write")
+        C.memset(self.REG_read, 0, 1024)
+        C.memset(self.REG_write, 0, 1024)
+        self.cfg = default_cfg(tic_period=tic_period)
+        self.L.correlator_init(C.c_double(tic_period))
+
+    # register accessors with the reference's masking (gp2021.c:11-14): data -> unsigned short
+    def _put(self, addr: int, data: int):
+        self.REG_write[addr] = data & 0xFFFF
+
+    def ch_cntl(self, ch, data):
+        self._put(ch << 3, data)
+
+    def ch_code_slew(self, ch, data):
+        self._put((ch << 3) + 0x84, data)
+
+    def ch_epoch_load(self, ch, data):
+        self._put((ch << 3) + 7, data)
+
+    def _nco(self, addr, freq, bits):
+        w = int(freq) << (32 - bits)
+        w = int(float(w) * self.cfg.clock_mult)
+        self._put(addr, w >> 16)
+        self._put(addr + 1, w & 0xFFFF)
+
+    def ch_carrier(self, ch, freq):
+        self._nco((ch << 3) + 3, freq, self.cfg.carrier_nco_bits)
+
+    def ch_code(self, ch, freq):
+        self._nco((ch << 3) + 5, freq, self.cfg.code_nco_bits)
+
+    def Sim_GP2021_int(self, IF: np.ndarray, nsamp: int):
+        buf = np.ascontiguousarray(IF, dtype=np.int8)
+        self.L.Sim_GP2021_int(buf.ctypes.data, nsamp)
+
+    def regs(self):
+        return np.array(self.REG_read[:], dtype=np.int32), np.array(self.REG_write[:], dtype=np.int32)
+
+
+class TrackingEngine:
+    """S independent receivers (IF streams) x 12 channels, closed loop on one GPU."""
+
+    def __init__(self, n_streams: int = 1, device: int = 0, cfg: abi.Cfg | None = None):
+        self.L = lib()
+        self.cfg = cfg if cfg is not None else default_cfg()
+        self.h = self.L.gnssb200_open(device, C.byref(self.cfg))
+        if not self.h:
+            raise GnssB200Error(
+                "gnssb200_open failed: " + (self.L.gnssb200_last_error_string() or b"?").decode()
+            )
+        self.n_streams = n_streams
+        check(self.L.gnssb200_set_streams(self.h, n_streams), "gnssb200_set_streams")
+        self.rx = (abi.Rx * n_streams)()
+        for s in range(n_streams):
+            self.L.gnssb200_rx_init(C.byref(self.rx[s]), C.byref(self.cfg))
+
+    def close(self):
+        if self.h:
+            self.L.gnssb200_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference-named host helpers, acting on the host copy of receiver `s` -------------
+    def simple_cold_allocate(self, s: int, prns):
+        arr = (C.c_int32 * abi.N_CHANNELS)(*prns)
+        self.L.gnssb200_rx_cold_allocate(C.byref(self.rx[s]), C.byref(self.cfg), arr)
+
+    def ch_cntl(self, s, ch, data):
+        self.L.gnssb200_ch_cntl(C.byref(self.rx[s]), ch, data)
+
+    def ch_carrier(self, s, ch, freq):
+        self.L.gnssb200_ch_carrier(C.byref(self.rx[s]), C.byref(self.cfg), ch, freq)
+
+    def ch_code(self, s, ch, freq):
+        self.L.gnssb200_ch_code(C.byref(self.rx[s]), C.byref(self.cfg), ch, freq)
+
+    def ch_code_slew(self, s, ch, data):
+        self.L.gnssb200_ch_code_slew(C.byref(self.rx[s]), ch, data)
+
+    def ch_epoch_load(self, s, ch, data):
+        self.L.gnssb200_ch_epoch_load(C.byref(self.rx[s]), ch, data)
+
+    def warm_start(self, s: int, ch: int, n_freq: int):
+        """Put a searching channel at the start of Doppler bin `n_freq`, as ch_acq
+        (osgpsisr.c:443-449) leaves it when it enters that bin."""
+        k = self.rx[s].chan[ch]
+        k.n_freq = n_freq
+        # del_freq sequence 1,-2,3,-4..: after reaching n the next step is -(2n) for n>0, 1-2n for n<=0
+        k.del_freq = -2 * n_freq if n_freq > 0 else 1 - 2 * n_freq
+        k.carrier_freq = self.cfg.gps_carrier_ref + k.carrier_cold_corr + self.cfg.d_freq * n_freq
+        k.codes = 0
+        self.ch_carrier(s, ch, k.carrier_freq)
+
+    def upload(self):
+        check(self.L.gnssb200_upload_rx(self.h, 0, self.n_streams, C.addressof(self.rx)), "gnssb200_upload_rx")
+
+    def download(self):
+        check(self.L.gnssb200_download_rx(self.h, 0, self.n_streams, C.addressof(self.rx)), "gnssb200_download_rx")
+
+    # ---- runs ----------------------------------------------------------------------------
+    def run_host(self, iq: np.ndarray, nblocks: int, nsamp: int = NSAMP_DEFAULT, fmt: int = abi.FMT_INT8_IQ,
+                 dump_cap: int = 0):
+        """iq: (S, bytes) host array.  Returns (dumps[S,12,cap], counts[S,12]) when dump_cap > 0."""
+        buf = np.ascontiguousarray(iq)
+        if buf.ndim == 1:
+            buf = buf.reshape(1, -1)
+        assert buf.shape[0] == self.n_streams
+        dumps = cnt = None
+        dp = cp = None
+        if dump_cap:
+            dumps = np.zeros((self.n_streams, abi.N_CHANNELS, dump_cap), dtype=abi.DUMP_DTYPE)
+            cnt = np.zeros((self.n_streams, abi.N_CHANNELS), dtype=np.int32)
+            dp, cp = dumps.ctypes.data, cnt.ctypes.data
+        check(
+            self.L.gnssb200_track_run_host(self.h, buf.ctypes.data, buf.strides[0], fmt, nsamp, nblocks, dp, dump_cap, cp),
+            "gnssb200_track_run_host",
+        )
+        return dumps, cnt
+
+    def run_device(self, d_if_ptr: int, stride: int, nblocks: int, nsamp: int = NSAMP_DEFAULT,
+                   fmt: int = abi.FMT_INT8_IQ, d_dumps_ptr: int = 0, dump_cap: int = 0, d_count_ptr: int = 0,
+                   stream: int = 0):
+        """Asynchronous run on device-resident samples (raw device pointers, e.g. tensor.data_ptr())."""
+        check(
+            self.L.gnssb200_track_run(self.h, d_if_ptr, stride, fmt, nsamp, nblocks, d_dumps_ptr or None, dump_cap,
+                                      d_count_ptr or None, stream or None),
+            "gnssb200_track_run",
+        )
+
+    def launch_count(self) -> int:
+        return int(self.L.gnssb200_launch_count(self.h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.L.gnssb200_last_kernel_ms(self.h))

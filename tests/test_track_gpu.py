@@ -1,0 +1,186 @@
+"""GPU parity of the correlator + channel loop against the oracle (bit exact, integer work).
+
+The oracle (oracle/gp2021_oracle.c) is itself pinned against the compiled reference in
+tests/test_oracle_vs_ref.py.  All calls go through the C ABI of libgnssb200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gnss_sdr_ru_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+NS = 8192
+PRNS = [27, 0, 0, 31, 0, 0, 0, 0, 9, 0, 32, 5]
+WARM = ((0, 1), (8, -1), (10, 1))
+
+
+def _rx_bytes(rx):
+    return bytes(memoryview(rx).cast("B"))
+
+
+def _setup_pair(oracle_lib, n_streams=1, cfg_over=None):
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+    from gnss_sdr_ru_b200.lib import default_cfg
+
+    cfg = default_cfg(**(cfg_over or {}))
+    eng = TrackingEngine(n_streams=n_streams, cfg=cfg)
+    orcs = []
+    for s in range(n_streams):
+        o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(**(cfg_over or {})))
+        o.cold_allocate(PRNS)
+        eng.simple_cold_allocate(s, PRNS)
+        for ch, nf in WARM:
+            eng.warm_start(s, ch, nf)
+            k = o.rx.chan[ch]
+            k.n_freq = nf
+            k.del_freq = -2 * nf if nf > 0 else 1 - 2 * nf
+            k.carrier_freq = o.cfg.gps_carrier_ref + o.cfg.d_freq * nf
+            k.codes = 0
+            o.ch_carrier(ch, k.carrier_freq)
+        assert _rx_bytes(eng.rx[s]) == _rx_bytes(o.rx)
+        orcs.append(o)
+    eng.upload()
+    return eng, orcs
+
+
+def _compare_run(eng, orcs, recs, nblk, fmt=abi.FMT_INT8_IQ, packed=None, cap=4000):
+    dumps, cnt = eng.run_host(packed if packed is not None else recs, nblk, NS, fmt, dump_cap=cap)
+    eng.download()
+    for s, o in enumerate(orcs):
+        n, odumps, ocnt = o.run(recs[s], NS, nblk, dump_cap=cap)
+        assert n == nblk
+        assert np.array_equal(cnt[s], ocnt), (cnt[s], ocnt)
+        for ch in range(12):
+            a, b = dumps[s, ch, : cnt[s, ch]], odumps[ch, : ocnt[ch]]
+            if not np.array_equal(a, b):
+                for f in a.dtype.names:
+                    bad = np.nonzero(np.atleast_1d((a[f] != b[f])).reshape(len(a), -1).any(axis=1))[0]
+                    if len(bad):
+                        i = bad[0]
+                        raise AssertionError(f"stream {s} ch {ch} field {f} first mismatch at dump {i}: gpu {a[i]} oracle {b[i]}")
+        got, want = eng.rx[s], o.rx
+        for name, _ in abi.Rx._fields_:
+            ga, wa = getattr(got, name), getattr(want, name)
+            gb = bytes(memoryview(ga).cast("B")) if hasattr(ga, "_length_") or isinstance(ga, C.Structure) else ga
+            wb = bytes(memoryview(wa).cast("B")) if hasattr(wa, "_length_") or isinstance(wa, C.Structure) else wa
+            assert gb == wb, f"stream {s}: rx.{name} differs after the run"
+    return dumps, cnt
+
+
+def test_closed_loop_short(oracle_lib, track_record):
+    rec, _ = track_record
+    eng, orcs = _setup_pair(oracle_lib)
+    _compare_run(eng, orcs, rec[None, : 2 * NS * 300], 300)
+
+
+def test_closed_loop_acq_pullin_track(oracle_lib, track_record):
+    rec, nblk = track_record
+    eng, orcs = _setup_pair(oracle_lib)
+    dumps, cnt = _compare_run(eng, orcs, rec[None, :], nblk)
+    states = [int(eng.rx[0].chan[ch].state) for ch in range(12)]
+    assert states[0] == 4 and states[8] == 4 and states[10] == 4, states  # all three reached CHANNEL_TRACKING
+
+
+def test_closed_loop_resume(oracle_lib, track_record):
+    """Two consecutive runs continue from the device-resident state (blocks_done advances)."""
+    rec, _ = track_record
+    eng, orcs = _setup_pair(oracle_lib)
+    _compare_run(eng, orcs, rec[None, : 2 * NS * 200], 200)
+    _compare_run(eng, orcs, rec[None, 2 * NS * 200 : 2 * NS * 500], 300)
+    assert eng.rx[0].blocks_done == 500
+
+
+def test_closed_loop_packed2(oracle_lib, track_record):
+    from gnss_sdr_ru_b200.synth import pack2
+
+    rec, _ = track_record
+    n = 600
+    eng, orcs = _setup_pair(oracle_lib)
+    sub = rec[: 2 * NS * n]
+    _compare_run(eng, orcs, sub[None, :], n, fmt=abi.FMT_PACKED2, packed=pack2(sub)[None, :])
+
+
+def test_closed_loop_multi_stream(oracle_lib, track_record):
+    rec, _ = track_record
+    n, S = 250, 5
+    recs = np.stack([np.roll(rec[: 2 * NS * n], 2 * 977 * s) for s in range(S)])
+    eng, orcs = _setup_pair(oracle_lib, n_streams=S)
+    _compare_run(eng, orcs, recs, n)
+
+
+def test_closed_loop_tic_and_thresholds(oracle_lib, track_record):
+    """TIC latches enabled (tic_period = 0.1 s), other block size, low threshold (false alarms)."""
+    rec, _ = track_record
+    over = dict(tic_period=0.01, acq_thresh=900)
+    eng, orcs = _setup_pair(oracle_lib, cfg_over=over)
+    global NS
+    old = NS
+    try:
+        NS = 6000
+        _compare_run(eng, orcs, rec[None, : 2 * NS * 400], 400)
+    finally:
+        NS = old
+
+
+def _poke(rng, tgt_put, o, step):
+    """random host writes between blocks, applied identically to both sides"""
+    ch = int(rng.integers(0, 12))
+    kind = int(rng.integers(0, 8))
+    if kind == 0:
+        v = int(rng.integers(0, 33))
+        tgt_put("cntl", ch, v)
+    elif kind == 1:
+        v = int(o.cfg.gps_carrier_ref + rng.integers(-70000, 70000))
+        tgt_put("carrier", ch, v)
+    elif kind == 2:
+        v = int(o.cfg.gps_code_ref + rng.integers(-3000, 3000))
+        tgt_put("code", ch, v)
+    elif kind == 3:
+        tgt_put("slew", ch, int(rng.integers(0, 5)))
+    elif kind == 4:
+        tgt_put("epoch", ch, int(rng.integers(0, 50 * 256)))
+    elif kind == 5 and step % 7 == 0:
+        tgt_put("slew", ch, int(rng.integers(0, 3000)))  # large slews: second table row / serial path
+    elif kind == 6 and step % 11 == 0:
+        tgt_put("code", ch, int(o.cfg.gps_code_ref * int(rng.integers(2, 40))))  # several dumps per block
+
+
+@pytest.mark.parametrize("nsamp,tic", [(8192, 0.0), (5000, 0.004), (16000, 0.1), (777, 0.0)])
+def test_dropin_random_registers(oracle_lib, nsamp, tic):
+    """Sim_GP2021_int through the reference's own symbols, random register traffic, every register
+    compared after every call."""
+    from gnss_sdr_ru_b200.receiver import DropInCorrelator
+
+    rng = np.random.default_rng(nsamp)
+    d = DropInCorrelator(tic_period=tic)
+    o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(tic_period=tic))
+
+    def put(kind, ch, v):
+        getattr(d, {"cntl": "ch_cntl", "carrier": "ch_carrier", "code": "ch_code", "slew": "ch_code_slew", "epoch": "ch_epoch_load"}[kind])(ch, v)
+        getattr(o, {"cntl": "ch_cntl", "carrier": "ch_carrier", "code": "ch_code", "slew": "ch_code_slew", "epoch": "ch_epoch_load"}[kind])(ch, v)
+
+    for ch in range(12):
+        put("cntl", ch, [27, 3, 0, 31, 32, 1, 0, 12, 9, 0, 32, 5][ch])
+        put("carrier", ch, int(o.cfg.gps_carrier_ref + 1000 * ch))
+        put("code", ch, int(o.cfg.gps_code_ref))
+    nblk = 260 if nsamp >= 5000 else 400
+    for b in range(nblk):
+        iq = rng.choice(np.array([-3, -1, 1, 3], dtype=np.int8), size=2 * nsamp)
+        if b % 50 == 0:
+            iq = rng.integers(-128, 128, size=2 * nsamp).astype(np.int8)  # any int8 works
+        d.Sim_GP2021_int(iq, nsamp)
+        o.sim(iq, nsamp)
+        rr, rw = d.regs()
+        orr, orw = np.array(o.rx.reg_read[:]), np.array(o.rx.reg_write[:])
+        assert np.array_equal(rr, orr), (b, np.nonzero(rr != orr)[0], rr[rr != orr], orr[rr != orr])
+        assert np.array_equal(rw, orw), (b, np.nonzero(rw != orw)[0])
+        # emulate what gpsisr does most often, then random pokes
+        st = rr[0x82]
+        for ch in range(12):
+            if st & (1 << ch) and rng.random() < 0.5:
+                put("slew", ch, 1)
+        for _ in range(int(rng.integers(0, 3))):
+            _poke(rng, put, o, b)
