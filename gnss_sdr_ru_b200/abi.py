@@ -128,6 +128,22 @@ class Dump(C.Structure):
     ]
 
 
+class SynthSat(C.Structure):
+    _fields_ = [
+        ("system", C.c_int32),
+        ("prn", C.c_int32),
+        ("cn0_dbhz", C.c_double),
+        ("samp_rate", C.c_double),
+        ("carrier_hz", C.c_double),
+        ("code_hz", C.c_double),
+        ("code_phase_chips", C.c_double),
+        ("carrier_phase_cycles", C.c_double),
+        ("data_seed", C.c_int32),
+        ("pad_", C.c_int32),
+        ("data_rate_hz", C.c_double),
+    ]
+
+
 class AcqCfg(C.Structure):
     _fields_ = [
         ("system", C.c_int32),

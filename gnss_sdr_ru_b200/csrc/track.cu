@@ -441,7 +441,13 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
   const int my_i0 = tid * SPT;
   if (sp_s.mode != MODE_STOP && my_i0 < a.nsamp) load_chunk<SPT>(stream_base, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, cur);
 
+#ifdef TRACK_PROFILE
+  long long t_main = 0, t_red = 0, t_isr = 0, t_sync2 = 0, t_corr = 0;
+#endif
   for (long long b = 0; b < a.nblocks; b++) {
+#ifdef TRACK_PROFILE
+    long long c0 = clock64();
+#endif
     const StepParams sp = sp_s;
     if (sp.mode == MODE_STOP) break;
     const uint8_t *blk = stream_base + (size_t)b * blk_bytes;
@@ -468,9 +474,15 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
           hl = h;
         }
         int pE = 0, pP = 0, pL = 0;
+#ifdef TRACK_PROFILE
+        long long cc0 = clock64();
+#endif
         if (live)
           correlate_chunk<SPT>(cur, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc, tbl, h, tbl[hl],
                                lut, pE, pP, pL);
+#ifdef TRACK_PROFILE
+        t_corr += clock64() - cc0 + (pE & 0);
+#endif
         const bool straddle = !allA && !allB;
         if (!straddle && live) {
           int v[6];
@@ -537,7 +549,13 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
     } else if (b + 1 < a.nblocks && my_i0 < a.nsamp) {
       load_chunk<SPT>(blk + blk_bytes, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, nxt);
     }
+#ifdef TRACK_PROFILE
+    long long c1 = clock64();
+#endif
     __syncthreads();
+#ifdef TRACK_PROFILE
+    long long c2 = clock64();
+#endif
 
     if (warp == 0) {
       int A[6], B[6];
@@ -568,10 +586,22 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
           prepare_block(cs, sp_s, a, tbl_prn);
       }
     }
+#ifdef TRACK_PROFILE
+    long long c3 = clock64();
+#endif
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < SPT / 2; q++) cur[q] = nxt[q];
+#ifdef TRACK_PROFILE
+    long long c4 = clock64();
+    t_main += c1 - c0; t_red += c2 - c1; t_isr += c3 - c2; t_sync2 += c4 - c3;
+#endif
   }
+#ifdef TRACK_PROFILE
+  if (blockIdx.x == 0 && (tid == 0 || tid == 37 || tid == 255))
+    printf("tid %d: main %lld (corr %lld)  sync1 %lld  isr %lld  sync2 %lld cycles/block\n", tid, t_main / a.nblocks,
+           t_corr / a.nblocks, t_red / a.nblocks, t_isr / a.nblocks, t_sync2 / a.nblocks);
+#endif
 
   if (tid == 0) {
     rx->chan[ch] = cs.k;

@@ -188,6 +188,31 @@ int64_t gnssb200_launch_count(const gnssb200_handle *h);
 float gnssb200_last_kernel_ms(gnssb200_handle *h);
 
 /* ---------------------------------------------------------------------------------------------
+ * synthetic IF records generated on the device (bench / test input, not part of the hot path).
+ * Signal model of SIM/glonass_l3_generator.sce:60-186 + AWGN: per emitter
+ * A*code(t)*data(t)*exp(-i(2*pi*f*t+phi0)), A = sqrt(10^(CN0/10)/fs), unit-power complex noise,
+ * 2-bit quantiser -> {-3,-1,+1,+3}.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gnssb200_synth_sat {
+  int32_t system;           /* GNSSB200_SYS_GPS (0) / GNSSB200_SYS_GLONASS (1) */
+  int32_t prn;              /* GPS PRN 1..32 (ignored for GLONASS: one ST code) */
+  double cn0_dbhz;          /* <= 0: emitter absent */
+  double samp_rate;
+  double carrier_hz;        /* IF + Doppler */
+  double code_hz;           /* chipping rate including code Doppler */
+  double code_phase_chips;  /* code phase of sample 0 */
+  double carrier_phase_cycles;
+  int32_t data_seed;        /* 0: no data modulation */
+  int32_t pad_;
+  double data_rate_hz;      /* 50 (GPS) / 100 (GLONASS meander) */
+} gnssb200_synth_sat;
+
+/* sats: [n_streams * n_sats].  fmt INT8_IQ or PACKED2; n_samples multiple of 4.  Synchronous. */
+int gnssb200_synth(gnssb200_handle *h, void *d_out, size_t stream_stride_bytes, int fmt, int n_streams,
+                   int64_t n_samples, const gnssb200_synth_sat *sats, int n_sats, uint64_t seed,
+                   void *cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
  * (2) batched layer -- FFT parallel-code-phase acquisition
  *     modelled on acqResults = acquisition(longSignal, settings)
  *     SCI/GLONASS/L1/acquisition.sci:1-198, SCI/GPS/L1/acquisition.sci
