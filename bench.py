@@ -1,0 +1,514 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 GNSS baseband engine (and of the reference CPU path).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own C receiver on host cores
+
+Metric (BASELINE.json): tracking channel*Msamples/s = streams x 12 channels x complex samples / time,
+closed loop (correlator + channel logic) included.  Workload: BASELINE config 5 sharded the way the
+config says -- 8 independent synthetic IF streams x 12 channels x 10 s per GPU (weak scaling; at
+N=8 this is exactly the 64-stream configuration).  One step = one pass of the whole workload.
+Acquisition cells/s for configs 1, 3 and 4 are measured outside the timed steps and reported under
+"acq" in the same JSON line.
+
+`value`  : inputs already resident in HBM, device-timed (CUDA events on the launching stream).
+`e2e`    : the same pass through the C ABI call that takes HOST buffers
+           (gnssb200_track_run_host: pinned host record -> H2D -> kernels -> D2H of the dump records).
+`roofline`: HBM form, algorithmic bytes = 0.5 B (packed 2+2 bit) or 2 B (int8) per complex sample per
+           stream, divided by the tracking kernel's launch duration; see DESIGN.md for why this path
+           is integer-issue bound long before it is HBM bound.
+`cpu_baseline`: the reference C receiver (oracle/_ref, compiled from the reference's own sources) on
+           one host core, on stream 0 of this rank's workload copied back from the GPU; its dump
+           records are also compared bit for bit with the GPU's.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NS = 8192  # complex samples per block, OSG/osgnss_next_step.c:150
+FS = 16_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams-per-gpu", type=int, default=8)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--fmt", default="packed2", choices=["packed2", "int8"])
+    ap.add_argument("--no-acq", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="length of the stream sample the CPU baseline processes")
+    ap.add_argument("--ref-sample-seconds", type=float, default=1.0, help="per-stream sample of the reference arm")
+    ap.add_argument("--gen-records", default=None, help=argparse.SUPPRESS)  # internal: write record files and exit
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, same fields as the
+    nvidia-smi line of B200_PROFILING.md: clocks.sm, clocks.max.sm, clocks_event_reasons.*)."""
+
+    def __init__(self, gpu_index: int):
+        import threading
+
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES-free torchrun launches: LOCAL_RANK == physical index on this box
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        bits = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.ok:
+            self._thread.start()
+
+    def stop(self):
+        if self.ok:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic_per_sample(fmt: str):
+    """DRAM bytes per complex stream-sample of the tracking kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get(f"track_dram_bytes_per_stream_sample_{fmt}")
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the reference's own C receiver (oracle/_ref) on all host cores, one process per
+    stream, on a bounded per-stream sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from multiprocessing import get_context
+
+    from oracle import oracle_api
+
+    oracle_api.build()
+    n_streams = args.streams_per_gpu * args.gpus
+    cores = os.cpu_count() or 1
+    workers = min(cores, n_streams)
+    nblk = int(args.ref_sample_seconds * FS / NS)
+    # input: stream records from the same scenario generator as our arm.  Generated in a child process so
+    # that this process never initialises CUDA before it forks its workers.
+    from gnss_sdr_ru_b200.scenarios import gps_tracking_scenario
+
+    n_rec = min(n_streams, workers)
+    tmp = tempfile.mkdtemp(prefix="gnssb200_ref_")
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--gen-records", tmp, "--streams-per-gpu", str(n_rec),
+                    "--ref-sample-seconds", str(args.ref_sample_seconds)], check=True, timeout=600)
+    recs = [(np.load(os.path.join(tmp, f"rec{i}.npy")), gps_tracking_scenario(5000 + i)) for i in range(n_rec)]
+    ctx = get_context("fork")
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with ctx.Pool(workers) as pool:
+            res = pool.map(_ref_worker, [(recs[i % len(recs)][0], recs[i % len(recs)][1], nblk) for i in range(workers)])
+        dt = max(r for r in res)  # processing time of the slowest worker (pool start-up excluded)
+        wall = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    value = workers * 12 * NS * nblk / t / 1e6
+    line = {
+        "impl": "reference", "metric": "tracking channel*Msamples/s", "value": value, "unit": "channel*Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"C5 shard: {args.streams_per_gpu} streams x 12 ch per GPU, GPS L1 C/A closed-loop tracking",
+                   "sample": f"{workers} streams x {args.ref_sample_seconds:g} s each (one process per stream)"},
+        "cpu_baseline": {"value": value, "unit": "channel*Msamples/s", "cores": workers, "kind": "reference",
+                         "sample": f"{workers} streams x 12 ch x {args.ref_sample_seconds:g} s, reference C receiver (gcc -O2), one process per stream"},
+        "e2e": {"value": value, "unit": "channel*Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def _ref_worker(job):
+    rec, sc, nblk = job
+    from oracle import oracle_api
+
+    ref = oracle_api.RefReceiver()
+    ref.cold_allocate(sc.prns)
+    for ch, (prn, n) in enumerate(zip(sc.prns, sc.n_freq)):
+        if prn > 0:
+            ref.warm_start(ch, n)
+    t0 = time.perf_counter()
+    ref.run(rec, NS, nblk)
+    return time.perf_counter() - t0
+
+
+def make_host_records(n, nblk, seed0):
+    """int8 records for the reference arm: device generator when a GPU is present, numpy otherwise."""
+    from gnss_sdr_ru_b200.scenarios import gps_tracking_scenario, synth_sat_array
+
+    scs = [gps_tracking_scenario(seed0 + s) for s in range(n)]
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            from gnss_sdr_ru_b200 import abi
+            from gnss_sdr_ru_b200.lib import check, lib
+
+            L = lib()
+            h = L.gnssb200_open(0, None)
+            buf = torch.empty((n, 2 * NS * nblk), dtype=torch.int8, device="cuda")
+            arr, nsat = synth_sat_array(scs)
+            check(L.gnssb200_synth(h, buf.data_ptr(), buf.stride(0), abi.FMT_INT8_IQ, n, NS * nblk, C.addressof(arr), nsat, 1234, None), "synth")
+            host = buf.cpu().numpy()
+            L.gnssb200_close(h)
+            return [(host[i], scs[i]) for i in range(n)]
+    except Exception:
+        pass
+    from gnss_sdr_ru_b200.synth import make_record
+
+    return [(make_record(scs[i].sats, NS * nblk, seed=seed0 + i), scs[i]) for i in range(n)]
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gnss_sdr_ru_b200 import abi
+    from gnss_sdr_ru_b200.lib import check, lib
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+    from gnss_sdr_ru_b200.scenarios import apply_tracking_scenario, gps_tracking_scenario, synth_sat_array
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    S = args.streams_per_gpu
+    nblk = int(args.seconds * FS / NS)  # 19531 for 10 s
+    fmt = abi.FMT_PACKED2 if args.fmt == "packed2" else abi.FMT_INT8_IQ
+    bytes_per_sample = 0.5 if fmt == abi.FMT_PACKED2 else 2.0
+    stream_bytes = int(NS * nblk * bytes_per_sample)
+    L = lib()
+    eng = TrackingEngine(n_streams=S, device=local)
+    scs = [gps_tracking_scenario(5000 + rank * S + s) for s in range(S)]
+    d_if = torch.empty((S, stream_bytes), dtype=torch.uint8, device=dev)
+    arr, nsat = synth_sat_array(scs)
+    check(L.gnssb200_synth(eng.h, d_if.data_ptr(), d_if.stride(0), fmt, S, NS * nblk, C.addressof(arr), nsat, 1234 + rank, None), "gnssb200_synth")
+
+    def reset_state():
+        for s in range(S):
+            L.gnssb200_rx_init(C.byref(eng.rx[s]), C.byref(eng.cfg))
+            apply_tracking_scenario(eng, s, scs[s])
+        eng.upload()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    kernel_ms = []
+
+    def step():
+        reset_state()
+        eng.run_device(d_if.data_ptr(), d_if.stride(0), nblk, NS, fmt, stream=stream.cuda_stream)
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        stream.synchronize()
+        kernel_ms.append(eng.last_kernel_ms())
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    t_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms_max = float(t.item())
+    total_chan_samples = world * S * 12 * NS * nblk
+    value = total_chan_samples * args.steps / (t_ms_max * 1e-3) / 1e6
+    eng.download()
+    states = [int(eng.rx[s].chan[ch].state) for s in range(S) for ch in range(12)]
+
+    # ---- end to end through the host-buffer C ABI call ----
+    h_if = torch.empty((S, stream_bytes), dtype=torch.uint8).pin_memory()
+    h_if.copy_(d_if)
+    cap = int(args.seconds * 1000) + 64
+    h_dumps = torch.empty((S, 12, cap, 48), dtype=torch.uint8).pin_memory()
+    h_cnt = torch.zeros((S, 12), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        reset_state()
+        h_cnt.zero_()
+        check(L.gnssb200_track_run_host(eng.h, h_if.data_ptr(), h_if.stride(0), fmt, NS, nblk, h_dumps.data_ptr(), cap, h_cnt.data_ptr()),
+              "gnssb200_track_run_host")
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_chan_samples * args.steps / float(te.item()) / 1e6
+    h2d = S * stream_bytes + S * C.sizeof(abi.Rx)
+    d2h = S * 12 * cap * 48 + S * 12 * 4
+
+    # ---- roofline of the tracking kernel ----
+    peak, peak_src = load_peaks()
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    alg_bytes = S * NS * nblk * bytes_per_sample
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    tr = measured_traffic_per_sample(args.fmt)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (tr * S * NS * nblk) if tr else None, "peak_source": peak_src,
+                "kernel": "track_loop_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "integer-issue bound, not HBM bound: ~20 issue slots per channel-sample x 12 channels per 0.5-2 B of input (DESIGN.md)"}
+
+    # ---- acquisition (configs 1, 3, 4), outside the timed steps ----
+    acq = None
+    if not args.no_acq:
+        acq = bench_acquisition(eng, dev, rank, world, clocks)
+
+    # ---- CPU baseline (rank 0): reference C receiver on stream 0, plus bit-exact check of the GPU dumps ----
+    cpu = None
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        cpu, parity = cpu_baseline(args, d_if, fmt, scs[0], h_dumps, h_cnt, nblk)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "tracking channel*Msamples/s", "value": value, "unit": "channel*Msamples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"C5 shard: {S} streams x 12 ch x {args.seconds:g} s per GPU, GPS L1 C/A closed-loop tracking "
+                               f"(search/confirm/pull-in/track), 8192-sample blocks",
+                   "input_format": args.fmt, "l2": "inputs larger than L2 (%.0f MB per GPU per step)" % (S * stream_bytes / 1e6),
+                   "streams_per_gpu": S, "blocks_per_stream": nblk,
+                   "channels_tracking_at_end": sum(1 for x in states if x == 4), "channels": len(states)},
+        "e2e": {"value": e2e_value, "unit": "channel*Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity_vs_reference": parity,
+        "acq": acq,
+    }
+    print(json.dumps(line))
+
+
+def bench_acquisition(eng, dev, rank, world, clocks):
+    """acq cells/s for BASELINE configs 1, 3, 4 on device-resident records.  With several ranks the
+    (sv, bin) grid is sharded (row r -> rank r % world) and the row tables are all-gathered (NCCL)."""
+    import torch
+    import torch.distributed as dist
+
+    from gnss_sdr_ru_b200 import abi
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.lib import check, lib
+    from gnss_sdr_ru_b200.scenarios import gps_acq_scenario, glonass_acq_scenario, gps_weak_acq_scenario, TrackScenario, synth_sat_array
+
+    L = lib()
+    ae = AcquisitionEngine(handle=eng.h)
+    sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
+    out = {}
+    N = 16000
+    cases = [
+        ("C1_gps_1ms_32prn_41bins", Settings.gps(acqSearchBand=20.0, acqCohIntegration=1), gps_acq_scenario(1001), 1001,
+         dict(B=2, K=1, T=1)),
+        ("C3_glonass_5ms_14fch_121bins", Settings.glonass(), glonass_acq_scenario(3003), 3003, dict(B=2, K=1, T=5)),
+        ("C4_gps_10ms_x20_32prn_401bins", Settings.gps(acqSearchBand=20.0, acqCohIntegration=10, n_noncoh=20),
+         gps_weak_acq_scenario(4004), 4004, dict(B=1, K=20, T=10)),
+    ]
+    for name, st, sats, seed, fl in cases:
+        n = ae.samples_needed(st)
+        n4 = (n + 3) // 4 * 4
+        rec = torch.empty(2 * n4, dtype=torch.uint8, device=dev)
+        arr, nsat = synth_sat_array([TrackScenario(sats=sats, prns=[], n_freq=[])])
+        check(L.gnssb200_synth(eng.h, rec.data_ptr(), 2 * n4, abi.FMT_INT8_IQ, 1, n4, C.addressof(arr), nsat, seed, None), "synth")
+        nb = ae.num_bins(st)
+        n_sv = len(st.acqSatelliteList)
+        rows = torch.zeros(n_sv * nb * 16, dtype=torch.uint8, device=dev)
+        reps = 3
+        times = []
+        for it in range(reps + 1):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            ae.search_device(rec.data_ptr(), n4, st, rows.data_ptr(), part_index=rank, part_count=world)
+            if world > 1:
+                # merge partitions: all-gather the row tables, keep the rows each rank owns
+                gathered = torch.empty(world * rows.numel(), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(gathered, rows)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                times.append(dt)
+        t = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            g = gathered.cpu().numpy().view(abi.ACQ_ROW_DTYPE).reshape(world, n_sv * nb)
+            merged = g[np.arange(n_sv * nb) % world, np.arange(n_sv * nb)]
+        else:
+            merged = rows.cpu().numpy().view(abi.ACQ_ROW_DTYPE)
+        res, amb = ae.finalize(st, merged)
+        found = sorted(int(r.sv) for r in res if r.sv != 0 or (st.system == "glonass" and r.peakMetric > st.acqThreshold))
+        cells = n_sv * nb * N
+        G = n_sv * nb
+        flops = fl["B"] * fl["K"] * (nb * (8 * fl["T"] * N + 5 * N * np.log2(N)) + G * (6 * N + 5 * N * np.log2(N) + 3 * N))
+        tt = float(t.item())
+        out[name] = {"cells": cells, "cells_per_s": cells / tt, "ms": tt * 1e3, "kernel_ms_rank0": ae.last_kernel_ms(),
+                     "algorithmic_gflop": flops / 1e9, "fp32_tflops_achieved": flops / tt / 1e12,
+                     "fp32_peak_tflops": fp32_peak, "fp32_frac": flops / tt / 1e12 / fp32_peak,
+                     "detected": found, "n_present": len(sats)}
+    return out
+
+
+def cpu_baseline(args, d_if, fmt, sc0, h_dumps, h_cnt, nblk):
+    from gnss_sdr_ru_b200 import abi
+    from gnss_sdr_ru_b200.synth import unpack2
+    from oracle import oracle_api
+
+    oracle_api.build()
+    nb = min(nblk, int(args.cpu_seconds * FS / NS))
+    raw = d_if[0].cpu().numpy()
+    if fmt == abi.FMT_PACKED2:
+        rec = unpack2(raw[: NS * nb // 2])
+    else:
+        rec = raw[: 2 * NS * nb].view(np.int8)
+    cap = h_dumps.shape[2]
+    kind = "reference" if oracle_api.have_ref() else "port"
+    if kind == "reference":
+        ref = oracle_api.RefReceiver()
+        ref.cold_allocate(sc0.prns)
+        for ch, (prn, n) in enumerate(zip(sc0.prns, sc0.n_freq)):
+            if prn > 0:
+                ref.warm_start(ch, n)
+        t0 = time.perf_counter()
+        n_done, dumps, cnt = ref.run(rec, NS, nb, dump_cap=cap)
+        dt = time.perf_counter() - t0
+    else:
+        o = oracle_api.Oracle()
+        o.cold_allocate(sc0.prns)
+        for ch, (prn, n) in enumerate(zip(sc0.prns, sc0.n_freq)):
+            if prn > 0:
+                k = o.rx.chan[ch]
+                k.n_freq = n
+                k.del_freq = -2 * n if n > 0 else 1 - 2 * n
+                k.carrier_freq = o.cfg.gps_carrier_ref + o.cfg.d_freq * n
+                o.ch_carrier(ch, k.carrier_freq)
+        t0 = time.perf_counter()
+        n_done, dumps, cnt = o.run(rec, NS, nb, dump_cap=cap)
+        dt = time.perf_counter() - t0
+    value = 12 * NS * nb / dt / 1e6
+    # parity: every dump record of stream 0 within the sampled blocks
+    g = h_dumps[0].numpy().view(abi.DUMP_DTYPE).reshape(12, cap)
+    gc = h_cnt[0].numpy()
+    ok, compared = True, 0
+    for ch in range(12):
+        a = g[ch, : gc[ch]]
+        a = a[a["block"] < nb]
+        b = dumps[ch, : cnt[ch]]
+        compared += len(b)
+        if len(a) != len(b) or not np.array_equal(a, b):
+            ok = False
+    cpu = {"value": value, "unit": "channel*Msamples/s", "cores": 1, "kind": kind,
+           "sample": f"stream 0 of rank 0: 12 channels x {nb * NS / FS:.2f} s ({nb} blocks), closed loop, gcc -O2, 1 thread"}
+    parity = {"bit_exact": bool(ok), "dump_records_compared": int(compared), "against": kind}
+    return cpu, parity
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.gen_records:
+        nblk_ = int(a.ref_sample_seconds * FS / NS)
+        for i_, (rec_, _) in enumerate(make_host_records(a.streams_per_gpu, nblk_, seed0=5000)):
+            np.save(os.path.join(a.gen_records, f"rec{i_}.npy"), rec_)
+    elif a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

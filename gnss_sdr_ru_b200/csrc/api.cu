@@ -145,6 +145,15 @@ extern "C" void gnssb200_close(gnssb200_handle *h) {
   cudaFree(h->d_rx);
   cudaFree(h->d_chan_flags);
   cudaFree(h->d_code_table);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->stage[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_used[i]) cudaEventDestroy(h->ev_used[i]);
+  }
+  cudaFree(h->stage_dumps);
+  cudaFree(h->stage_cnt);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_comp) cudaStreamDestroy(h->s_comp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -219,45 +228,100 @@ extern "C" int gnssb200_track_run(gnssb200_handle *h, const void *d_if, size_t s
   return 0;
 }
 
+// Host-buffer variant.  The record is streamed through two device staging buffers in chunks of
+// blocks: the H2D copy of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream);
+// receiver state stays on the device between chunks.  Pass pinned host memory for full PCIe speed.
 extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stride, int fmt, int nsamp, int64_t nblocks,
                                        gnssb200_dump *h_dumps, int dump_cap, int32_t *h_dump_count) {
   if (!h || h->n_streams <= 0) {
     gnssb200_set_error(-3, "gnssb200_track_run_host: no streams configured", __FILE__, __LINE__);
     return -3;
   }
+  if (fmt < 0 || fmt > 2 || nsamp <= 0 || (fmt == GNSSB200_FMT_PACKED2 && (nsamp & 1))) {
+    gnssb200_set_error(-4, "gnssb200_track_run_host: bad format / block size", __FILE__, __LINE__);
+    return -4;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   const int S = h->n_streams;
-  const size_t per_stream = fmt_bytes(fmt, (long long)nsamp * nblocks);
-  const size_t dstride = (per_stream + 255) & ~(size_t)255;
-  uint8_t *d_if = nullptr;
-  gnssb200_dump *d_dumps = nullptr;
-  int32_t *d_cnt = nullptr;
-  CUDA_TRY(cudaMalloc(&d_if, dstride * S + 256));
-  CUDA_TRY(cudaMemcpy2D(d_if, dstride, h_if, stride, per_stream, S, cudaMemcpyHostToDevice));
-  const bool want = h_dumps && dump_cap > 0;
-  if (want) {
-    CUDA_TRY(cudaMalloc(&d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap));
-    CUDA_TRY(cudaMalloc(&d_cnt, sizeof(int32_t) * S * NCH));
-    if (h_dump_count)
-      CUDA_TRY(cudaMemcpy(d_cnt, h_dump_count, sizeof(int32_t) * S * NCH, cudaMemcpyHostToDevice));
-    else
-      CUDA_TRY(cudaMemset(d_cnt, 0, sizeof(int32_t) * S * NCH));
-  }
-  int rc = gnssb200_track_run(h, d_if, dstride, fmt, nsamp, nblocks, d_dumps, want ? dump_cap : 0, d_cnt, nullptr);
-  if (!rc) {
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) {
-      gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
-      rc = (int)e;
+  const size_t blk_bytes = fmt_bytes(fmt, nsamp);
+  long long chunk = (long long)((32u << 20) / (blk_bytes * (size_t)S));  // ~32 MiB per staging buffer
+  if (chunk < 16) chunk = 16;
+  if (chunk > nblocks) chunk = nblocks;
+  const size_t dstride = (blk_bytes * (size_t)chunk + 255) & ~(size_t)255;
+  int rc = 0;
+  auto fail = [&](cudaError_t e, int line) {
+    gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, line);
+    rc = (int)e;
+  };
+#define TRY_(x)                         \
+  do {                                  \
+    cudaError_t e_ = (x);               \
+    if (e_ != cudaSuccess && !rc) fail(e_, __LINE__); \
+  } while (0)
+  if (!h->s_copy) {
+    TRY_(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    TRY_(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      TRY_(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      TRY_(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
     }
   }
-  if (!rc && want) {
-    cudaMemcpy(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost);
-    if (h_dump_count) cudaMemcpy(h_dump_count, d_cnt, sizeof(int32_t) * S * NCH, cudaMemcpyDeviceToHost);
+  if (!rc && dstride * S + 256 > h->stage_cap) {
+    for (int i = 0; i < 2; i++) {
+      cudaFree(h->stage[i]);
+      h->stage[i] = nullptr;
+      TRY_(cudaMalloc(&h->stage[i], dstride * S + 256));
+    }
+    h->stage_cap = rc ? 0 : dstride * S + 256;
   }
-  cudaFree(d_if);
-  cudaFree(d_dumps);
-  cudaFree(d_cnt);
+  const bool want = h_dumps && dump_cap > 0;
+  if (want && !rc) {
+    const size_t need = sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap;
+    if (need > h->stage_dumps_cap) {
+      cudaFree(h->stage_dumps);
+      h->stage_dumps = nullptr;
+      TRY_(cudaMalloc(&h->stage_dumps, need));
+      h->stage_dumps_cap = rc ? 0 : need;
+    }
+    if (sizeof(int32_t) * S * NCH > h->stage_cnt_cap) {
+      cudaFree(h->stage_cnt);
+      h->stage_cnt = nullptr;
+      TRY_(cudaMalloc(&h->stage_cnt, sizeof(int32_t) * S * NCH));
+      h->stage_cnt_cap = rc ? 0 : sizeof(int32_t) * S * NCH;
+    }
+  }
+  uint8_t **d_stage = h->stage;
+  gnssb200_dump *d_dumps = want ? h->stage_dumps : nullptr;
+  int32_t *d_cnt = want ? h->stage_cnt : nullptr;
+  cudaStream_t s_copy = h->s_copy, s_comp = h->s_comp;
+  cudaEvent_t *ev_copied = h->ev_copied, *ev_used = h->ev_used;
+  if (want && !rc) {
+    if (h_dump_count)
+      TRY_(cudaMemcpyAsync(d_cnt, h_dump_count, sizeof(int32_t) * S * NCH, cudaMemcpyHostToDevice, s_comp));
+    else
+      TRY_(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * S * NCH, s_comp));
+  }
+  if (!rc) TRY_(cudaEventRecord(h->ev0, s_comp));
+  int c = 0;
+  for (long long b0 = 0; b0 < nblocks && !rc; b0 += chunk, c++) {
+    const long long nb = (nblocks - b0 < chunk) ? nblocks - b0 : chunk;
+    const int buf = c & 1;
+    if (c >= 2) TRY_(cudaStreamWaitEvent(s_copy, ev_used[buf], 0));  // kernels of chunk c-2 are done with it
+    TRY_(cudaMemcpy2DAsync(d_stage[buf], dstride, (const uint8_t *)h_if + (size_t)b0 * blk_bytes, stride, blk_bytes * (size_t)nb, S,
+                           cudaMemcpyHostToDevice, s_copy));
+    TRY_(cudaEventRecord(ev_copied[buf], s_copy));
+    TRY_(cudaStreamWaitEvent(s_comp, ev_copied[buf], 0));
+    if (!rc) rc = track_launch(h, 0, S, d_stage[buf], dstride, fmt, nsamp, nb, 1, d_dumps, want ? dump_cap : 0, d_cnt, s_comp);
+    TRY_(cudaEventRecord(ev_used[buf], s_comp));
+  }
+  if (!rc) TRY_(cudaEventRecord(h->ev1, s_comp));
+  if (!rc && want) {
+    TRY_(cudaMemcpyAsync(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost, s_comp));
+    if (h_dump_count) TRY_(cudaMemcpyAsync(h_dump_count, d_cnt, sizeof(int32_t) * S * NCH, cudaMemcpyDeviceToHost, s_comp));
+  }
+  if (s_comp) TRY_(cudaStreamSynchronize(s_comp));
+  if (s_copy) TRY_(cudaStreamSynchronize(s_copy));
+#undef TRY_
   return rc;
 }
 

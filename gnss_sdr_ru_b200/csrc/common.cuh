@@ -33,6 +33,15 @@ struct gnssb200_handle {
   long long launches;
   // acquisition workspace (acq.cu)
   void *acq_ws;
+  // staging of gnssb200_track_run_host (api.cu), kept between calls
+  uint8_t *stage[2];
+  size_t stage_cap;
+  gnssb200_dump *stage_dumps;
+  size_t stage_dumps_cap;
+  int32_t *stage_cnt;
+  size_t stage_cnt_cap;
+  cudaStream_t s_copy, s_comp;
+  cudaEvent_t ev_copied[2], ev_used[2];
 };
 
 // track.cu

@@ -39,7 +39,7 @@ def lib() -> C.CDLL:
         raise GnssB200Error(
             f"{SO_PATH} is missing: build it with gnss_sdr_ru_b200/csrc/build.sh (there is no CPU fallback)"
         )
-    L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(SO_PATH)  # RTLD_LOCAL: the drop-in symbols must not interpose on other libraries in the process
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     P = C.POINTER
     L.gnssb200_last_error.restype = C.c_int

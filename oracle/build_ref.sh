@@ -52,10 +52,11 @@ gcc $CF -c "$SRC/isr/osgpsisr.c"         -o host_objs/osgpsisr.o
 gcc $CF -c "$SRC/osgnss_next_step.c"     -o host_objs/main.o
 gcc $CF -Dmain=osgnss_main -c "$SRC/osgnss_next_step.c" -o host_objs/main_lib.o
 gcc $CF -c display_stub.c                -o host_objs/display_stub.o
+gcc $CF -I"$HERE/.." -c "$HERE/ref_driver.c" -o host_objs/ref_driver.o
 gcc $CF -c "$SRC/correlator/correlator.c" -o correlator_ref.o
 sed 's/\[33\]\[2046\]/[34][2046]/g' "$SRC/correlator/correlator.c" | gcc $CF -x c -c - -o correlator_ref34.o
-gcc -shared -o libosgnss_ref.so   correlator_ref.o   host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main_lib.o host_objs/display_stub.o -lm
-gcc -shared -o libosgnss_ref34.so correlator_ref34.o host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main_lib.o host_objs/display_stub.o -lm
+gcc -shared -Wl,-Bsymbolic -o libosgnss_ref.so   correlator_ref.o   host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main_lib.o host_objs/display_stub.o host_objs/ref_driver.o -lm
+gcc -shared -Wl,-Bsymbolic -o libosgnss_ref34.so correlator_ref34.o host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main_lib.o host_objs/display_stub.o host_objs/ref_driver.o -lm
 gcc -o osgnss_ref   correlator_ref.o   host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main.o host_objs/display_stub.o -lm
 gcc -o osgnss_ref34 correlator_ref34.o host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main.o host_objs/display_stub.o -lm
 echo "built oracle/_ref: $(ls "$OUT" | tr '\n' ' ')"

@@ -177,8 +177,9 @@ class RefReceiver:
         path = REF_SO_PRISTINE if pristine else REF_SO
         if not os.path.exists(path):
             build()
-        # each instance gets a private copy of the .so so that several can coexist in one process
-        self.L = C.CDLL(path)
+        # DEEPBIND + -Bsymbolic: the reference's Sim_GP2021_int/REG_* must bind to the reference, even when
+        # libgnssb200.so (which exports the same drop-in symbols) lives in the same process
+        self.L = C.CDLL(path, mode=os.RTLD_LOCAL | getattr(os, "RTLD_DEEPBIND", 0))
         L = self.L
         L.correlator_init.argtypes = [C.c_double]
         L.Sim_GP2021_int.argtypes = [C.c_void_p, C.c_long]
@@ -229,3 +230,25 @@ class RefReceiver:
 
     def regs(self):
         return np.array(self.REG_read[:], dtype=np.int32), np.array(self.REG_write[:], dtype=np.int32)
+
+    def run(self, iq: np.ndarray, nsamp: int, nblocks: int, dump_cap: int = 0, block0: int = 0):
+        """Native loop (oracle/ref_driver.c) around the reference's Sim_GP2021_int + gpsisr."""
+        buf = np.ascontiguousarray(iq, dtype=np.int8)
+        assert buf.size >= 2 * nsamp * nblocks
+        self.L.ref_run.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_int, C.c_void_p]
+        self.L.ref_run.restype = C.c_long
+        if dump_cap:
+            dumps = np.zeros((abi.N_CHANNELS, dump_cap), dtype=abi.DUMP_DTYPE)
+            cnt = np.zeros(abi.N_CHANNELS, dtype=np.int32)
+            n = self.L.ref_run(buf.ctypes.data, nsamp, nblocks, block0, dumps.ctypes.data, dump_cap, cnt.ctypes.data)
+            return n, dumps, cnt
+        n = self.L.ref_run(buf.ctypes.data, nsamp, nblocks, block0, None, 0, None)
+        return n, None, None
+
+    def warm_start(self, ch: int, n_freq: int):
+        k = self.chan[ch]
+        k.n_freq = n_freq
+        k.del_freq = -2 * n_freq if n_freq > 0 else 1 - 2 * n_freq
+        k.carrier_freq = self.gps_carrier_ref.value + k.carrier_cold_corr + self.d_freq.value * n_freq
+        k.codes = 0
+        self.L.ch_carrier(ch, k.carrier_freq)
