@@ -68,6 +68,14 @@ static inline int tab_at(const int8_t *t, long flat) {
   return (flat >= 0 && flat < (long)TABLE_ROWS * HALF_CHIPS) ? t[flat] : 0;
 }
 
+/* 8-phase LO of the carrier mixer, OSG/correlator/correlator.c:203-204 (= NAM/rtl/carrier_nco.v:21-25) */
+static const int lo_i[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
+static const int lo_q[8] = {2, 2, 1, -1, -2, -2, -1, 1};
+void orc_lo_table(int phase, int out[2]) {
+  out[0] = lo_i[phase & 7];
+  out[1] = lo_q[phase & 7];
+}
+
 /* expose for tests: E/P/L at (prn, h) */
 void orc_code_bits(int prn, int h, int out[3]) {
   build_tables();
@@ -178,8 +186,6 @@ void orc_rx_cold_allocate(gnssb200_rx *rx, const gnssb200_cfg *c, const int32_t 
 /* ------------------------------------------------------------------------------------------- */
 /* Sim_GP2021_int: OSG/correlator/correlator.c:148-316                                            */
 void orc_sim_gp2021(gnssb200_rx *rx, const gnssb200_cfg *c, const int8_t *IF, long nsamp, int iq) {
-  static const int lo_i[8] = {-1, 1, 2, 2, 1, -1, -2, -2}; /* :203 */
-  static const int lo_q[8] = {2, 2, 1, -1, -2, -2, -1, 1}; /* :204 */
   int tic_count;
   int status = 0;
   build_tables();

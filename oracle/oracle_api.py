@@ -64,6 +64,7 @@ class Oracle:
             L.orc_ch_carrier.argtypes = [C.POINTER(abi.Rx), C.POINTER(abi.Cfg), C.c_int, C.c_int64]
             L.orc_ch_code.argtypes = [C.POINTER(abi.Rx), C.POINTER(abi.Cfg), C.c_int, C.c_int64]
             L.orc_code_bits.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int * 3)]
+            L.orc_lo_table.argtypes = [C.c_int, C.POINTER(C.c_int * 2)]
             cls._lib = L
         return cls._lib
 
@@ -125,6 +126,15 @@ class Oracle:
 
     def ch_epoch_load(self, ch, v):
         self.lib().orc_ch_epoch_load(C.byref(self.rx), ch, v)
+
+    @staticmethod
+    def lo_table():
+        out = (C.c_int * 2)()
+        tab = []
+        for k in range(8):
+            Oracle.lib().orc_lo_table(k, C.byref(out))
+            tab.append((out[0], out[1]))
+        return tab
 
     @staticmethod
     def code_bits(prn: int, h: int):

@@ -139,3 +139,17 @@ def test_acq_partition_merge(oracle_lib):
             merged[take] = pn[take]
     assert (merged["peak"] >= 0).all()
     assert np.array_equal(merged, full_np)
+
+
+def test_acq_vs_committed_fixture():
+    import os
+
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "acq_golden.npz"))
+    st = Settings.gps(acqSearchBand=float(g["band"]), acqCohIntegration=int(g["coh"]), acqSatelliteList=[int(x) for x in g["sv"]])
+    res = AcquisitionEngine().acquisition(g["packed"], st, fmt=abi.FMT_PACKED2, return_rows=True)
+    assert [int(x) for x in res["bin"]] == [int(x) for x in g["bin"]]
+    assert [int(x) for x in res["codePhaseRaw"]] == [int(x) for x in g["codePhaseRaw"]]
+    assert np.allclose(res["peakMetric"], g["peakMetric"], rtol=RTOL)
+    assert np.allclose(res["rows"]["peak"], g["rows"][:, :, 0], rtol=RTOL)

@@ -184,3 +184,24 @@ def test_dropin_random_registers(oracle_lib, nsamp, tic):
                 put("slew", ch, 1)
         for _ in range(int(rng.integers(0, 3))):
             _poke(rng, put, o, b)
+
+
+def test_closed_loop_vs_reference_golden():
+    """GPU vs the committed outputs of the compiled reference itself (tests/golden/ref_track_golden.npz)"""
+    import os
+
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_track_golden.npz"))
+    eng = TrackingEngine(n_streams=1)
+    eng.simple_cold_allocate(0, [int(p) for p in g["prns"]])
+    for ch, nf in g["warm"]:
+        eng.warm_start(0, int(ch), int(nf))
+    eng.upload()
+    cap = g["dumps"].shape[1]
+    dumps, cnt = eng.run_host(g["packed"][None, :], int(g["nblk"]), int(g["nsamp"]), abi.FMT_PACKED2, dump_cap=cap)
+    eng.download()
+    assert np.array_equal(cnt[0], g["cnt"])
+    assert np.array_equal(dumps[0], g["dumps"].view(abi.DUMP_DTYPE).reshape(dumps[0].shape))
+    assert np.array_equal(np.array(eng.rx[0].reg_read[:]), g["reg_read"])
+    assert np.array_equal(np.array(eng.rx[0].reg_write[:]), g["reg_write"])
