@@ -59,4 +59,12 @@ gcc -shared -Wl,-Bsymbolic -o libosgnss_ref.so   correlator_ref.o   host_objs/gp
 gcc -shared -Wl,-Bsymbolic -o libosgnss_ref34.so correlator_ref34.o host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main_lib.o host_objs/display_stub.o host_objs/ref_driver.o -lm
 gcc -o osgnss_ref   correlator_ref.o   host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main.o host_objs/display_stub.o -lm
 gcc -o osgnss_ref34 correlator_ref34.o host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main.o host_objs/display_stub.o -lm
+# drop-in demonstration: the reference's host side (main, gpsisr, gp2021 accessors) linked against
+# libgnssb200.so INSTEAD of correlator.c.  -rdynamic exports the host's globals (REG_*, gps_*_ref, ...)
+# so that the library's references bind to the executable's copies, as in the single-binary reference.
+GPULIB="$HERE/../gnss_sdr_ru_b200"
+if [ -f "$GPULIB/libgnssb200.so" ]; then
+  gcc -o osgnss_gpu host_objs/gp2021.o host_objs/osgpsisr.o host_objs/main.o host_objs/display_stub.o \
+      -L"$GPULIB" -lgnssb200 -Wl,-rpath,'$ORIGIN/../../gnss_sdr_ru_b200' -rdynamic -lm
+fi
 echo "built oracle/_ref: $(ls "$OUT" | tr '\n' ' ')"

@@ -30,7 +30,10 @@ def build(force: bool = False) -> None:
         os.path.join(HERE, "gp2021_oracle.c")
     ):
         subprocess.check_call(["make", "-C", HERE, os.path.join(HERE, "liboracle.so")], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_SO)):
+    gpu_bin = os.path.join(HERE, "_ref", "osgnss_gpu")
+    gpu_lib = os.path.join(os.path.dirname(HERE), "gnss_sdr_ru_b200", "libgnssb200.so")
+    stale = os.path.exists(gpu_lib) and (not os.path.exists(gpu_bin))
+    if os.path.isdir("/root/reference") and (force or stale or not os.path.exists(REF_SO)):
         subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
 
 
