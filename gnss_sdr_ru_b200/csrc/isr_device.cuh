@@ -26,7 +26,13 @@ __device__ __forceinline__ int reg16(int v) { return (int)(uint16_t)v; }  // out
 
 __device__ __forceinline__ void dev_put_nco(int &hi, int &lo, long long freq, int bits, double mult) {
   long long w = freq << (32 - bits);
-  w = (long long)((double)w * mult);  // gp2021.c:90-91 / 109-110
+  // gp2021.c:90-91 / 109-110: long * (double)5 -> long.  For an integral multiplier and abs(w) < 2^40 the
+  // product is exact in double, so the integer product is the same value.
+  const long long im = (long long)mult;
+  if ((double)im == mult && w > -(1ll << 40) && w < (1ll << 40) && im > -1024 && im < 1024)
+    w = w * im;
+  else
+    w = (long long)((double)w * mult);
   hi = reg16((int)(w >> 16));
   lo = reg16((int)(w & 0xffff));
 }
@@ -49,10 +55,34 @@ __device__ __forceinline__ long long dev_mag(long long a, long long b) {  // rss
   return (c > d) ? (d >> 1) + c : (c >> 1) + d;
 }
 
-__device__ __noinline__ unsigned dev_isqrt(long long L) {  // sqrt_newton()
+// trunc(a / b) for 64-bit integers.  For abs(a) < 2^52 the correctly rounded FP64 quotient cannot cross
+// an integer (a non-integer quotient is at least 1/abs(b) >= 2^-31 away from one, far more than the
+// 2^-53 relative rounding error), so FP64 division + truncation is exact; it is several times
+// shorter than the 64-bit integer division sequence on this GPU.
+__device__ __forceinline__ long long dev_div64(long long a, long long b) {
+  const long long aa = a < 0 ? -a : a;
+  if (aa < (1ll << 52) && b > -(1ll << 31) && b < (1ll << 31)) return (long long)((double)a / (double)b);
+  return a / b;
+}
+
+// sqrt_newton() (osgpsisr.c:148-178).  For every argument 0 < L < 2^31 -- the reference only passes
+// sums of two squared shorts -- the Newton iteration of the reference returns
+//        max { x : x*(x-1) <= L }
+// (verified exhaustively over all 2^31 - 1 arguments against the reference's own loop, see
+// tests/test_isr_math.py for the sampled regression).  So the value is taken from a float square root
+// and corrected with exact integer tests; larger arguments run the literal iteration.
+__device__ __forceinline__ unsigned dev_isqrt(long long L) {
+  if (L <= 0) return 0;
+  if (L < (1ll << 31)) {
+    const unsigned l = (unsigned)L;
+    unsigned x = (unsigned)(sqrtf((float)l) + 0.5f);
+    if (x == 0) x = 1;
+    while ((unsigned long long)x * (x - 1) > l) x--;
+    while ((unsigned long long)(x + 1) * x <= l) x++;
+    return x;
+  }
   long long t, div;
   unsigned r = (unsigned)L;
-  if (L <= 0) return 0;
   if (L & 0xFFFF0000LL)
     div = (L & 0xFF000000LL) ? 0x3FFF : 0x3FF;
   else
@@ -70,25 +100,32 @@ __device__ __noinline__ unsigned dev_isqrt(long long L) {  // sqrt_newton()
   }
 }
 
-__device__ __noinline__ long long dev_atan2(long long y, long long x) {  // fix_atan2(), 1 rad = 16384
+// fix_atan2() (osgpsisr.c:199-231), 1 rad = 16384.  The divisor is always the operand of larger
+// magnitude, so abs(n) <= 2^14 and the cubic correction fits 32-bit arithmetic; the one real division is
+// done in FP64 (exact, see dev_div64).
+__device__ __forceinline__ int dev_atan2_n3(int n) {  // ((((n*n)>>14)*n)>>13)/9 with abs(n) <= 2^14
+  return ((((n * n) >> 14) * n) >> 13) / 9;
+}
+__device__ __noinline__ long long dev_atan2(long long y, long long x) {
   const long long half_pi = 25736, pi = 51472;
-  long long n, n3, res = 0;
+  long long res = 0;
   if (x == 0 && y == 0) return 0;
+  const bool small = y > -(1ll << 31) && y < (1ll << 31) && x > -(1ll << 31) && x < (1ll << 31);
   if (x > 0 && x >= dev_abs_trunc(y)) {
-    n = (y << 14) / x;
-    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    const long long n = dev_div64(y << 14, x);
+    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
     res = n - n3;
   } else if (x <= 0 && -x >= dev_abs_trunc(y)) {
-    n = (y << 14) / x;
-    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    const long long n = dev_div64(y << 14, x);
+    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
     res = (y > 0) ? n - n3 + pi : n - n3 - pi;
   } else if (y > 0 && y > dev_abs_trunc(x)) {
-    n = (x << 14) / y;
-    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    const long long n = dev_div64(x << 14, y);
+    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
     res = half_pi - n + n3;
   } else if (y < 0 && -y > dev_abs_trunc(x)) {
-    n = (x << 14) / y;
-    n3 = ((((n * n) >> 14) * n) >> 13) / 9;
+    const long long n = dev_div64(x << 14, y);
+    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
     res = -n + n3 - half_pi;
   }
   return res;
@@ -179,11 +216,9 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
 
   if (ie != 0 && qe != 0 && il != 0 && ql != 0) {
     unsigned se = dev_isqrt((long long)(ie * ie + qe * qe)), sl = dev_isqrt((long long)(il * il + ql * ql));
-    long long e = (long long)se;
-    e = e - (long long)sl;
-    e = 8192 * e;
-    e = e / (long long)((int)se + (int)sl);
-    k.codeError = e;
+    // (8192*(se-sl))/(se+sl): se, sl <= 46341, so everything fits int32 (C division truncates toward zero)
+    const int num = 8192 * ((int)se - (int)sl);
+    k.codeError = (long long)(num / ((int)se + (int)sl));
   } else
     k.codeError = k.oldCodeError;
   k.codeNco = k.oldCodeNco + (((c.dll_i1 + 1) * k.codeError - c.dll_i2 * k.oldCodeError) / 8192);

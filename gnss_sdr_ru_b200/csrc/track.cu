@@ -7,17 +7,22 @@
 // the reference (each dump only touches its own registers and its own struct tracking_channel), so
 // a CTA runs its channel through all blocks without any grid-wide synchronisation:
 //
-//   per block:  every thread takes SPT consecutive complex samples (16-byte vector loads, next
-//               block prefetched into registers), starts its carrier/code NCOs from the closed form
-//               phase(i) = phase0 + i*incr, and walks its samples with the
-//               exact integer arithmetic of the reference: 8-phase LO (phase>>29), complex mix,
-//               +-1 E/P/L code taps at half-chip spacing, code-NCO carry -> next half chip.
+//   staging:    the block's samples are brought into shared memory by the TMA engine
+//               (cp.async.bulk + mbarrier, one elected thread), double buffered: block b+1 lands
+//               while block b is correlated and its ISR runs.  Packed 2-bit input is 4 KB per block.
+//   per block:  every thread takes 32 consecutive complex samples (128-bit shared-memory loads),
+//               starts its carrier/code NCOs from the closed form phase(i) = phase0 + i*incr
+//               (SURVEY.md Appendix A), and walks them with the exact integer arithmetic of the
+//               reference: 8-phase LO (phase>>29), complex mix, +-1 E/P/L taps at half-chip spacing.
 //               I and Q products ride in one 32-bit register as two 16-bit lanes (|sum| <= 32*384
-//               per thread), so the six MACs of the reference are three IMADs.
+//               per thread).  Samples are taken four at a time: with 4*kinc < 2^32 at most one
+//               code-NCO carry falls inside a group, so the group contributes
+//               old_bits*S_old + new_bits*S_new  -- 6 IMADs and one table read per 4 samples instead
+//               of 12 IMADs and 4 predicated reloads.
 //   dump:       at most one per block on this path; a chunk lies before, after or across it.  The
 //               (single) straddling chunk is re-evaluated sample-per-lane by its warp with the
 //               closed forms, so no thread carries two accumulator sets through its loop.
-//   reduce:     __reduce_add_sync (REDUX) per warp, 12 partials per warp through shared memory.
+//   reduce:     warp shuffles, then 12 x 8 partials through shared memory.
 //   ISR:        lane 0 of warp 0 applies the dump / TIC / epoch rules, runs the channel state
 //               machine (isr_device.cuh) and publishes next block's NCO words.
 //
@@ -38,6 +43,9 @@ struct StepParams {
   uint32_t hc0, w1, stale_idx, slew_dump;
   int mode;
   int tic_count;
+  uint32_t stale_bits;   // table entry at stale_idx
+  uint32_t cyc_pending;  // carrier wraps of quiet blocks not yet added to gnssb200_corr.carrier_cycle
+  long long tic;         // value of the TIC down-counter after this block's tic_count was derived
 };
 
 struct TrackArgs {
@@ -100,7 +108,24 @@ __device__ __forceinline__ void load_sample(const uint8_t *blk, int fmt, int i, 
 }
 
 // SPT consecutive samples starting at i0 -> SPT/2 words of (I0,Q0,I1,Q1) int8
-template <int SPT>
+// One packed byte (I0 Q0 I1 Q1 as 2-bit codes, LSB first) -> int8 word (I0,Q0,I1,Q1).  The four codes are
+// spread into selector nibbles and one PRMT picks the values {+1,-1,+3,-3} from a register table:
+// no shared-memory look-up, no bank conflicts.
+__device__ __forceinline__ uint32_t unpack_byte(uint32_t b) {
+  uint32_t x = (b | (b << 4)) & 0x0F0Fu;
+  x = (x | (x << 2)) & 0x3333u;
+  return __byte_perm(0xFD03FF01u, 0u, x);  // bytes: code0 -> 0x01, code1 -> 0xFF, code2 -> 0x03, code3 -> 0xFD
+}
+
+template <bool SMEM, class T>
+__device__ __forceinline__ T ld_in(const T *p) {
+  if constexpr (SMEM)
+    return *p;  // shared-memory tile written by the TMA engine
+  else
+    return __ldg(p);
+}
+
+template <int SPT, bool SMEM = false>
 __device__ __forceinline__ void load_chunk(const uint8_t *blk, int fmt, int i0, int nsamp, bool aligned,
                                            const uint32_t *unpack_lut, uint32_t (&w)[SPT / 2]) {
   if (i0 + SPT <= nsamp && aligned) {
@@ -108,7 +133,7 @@ __device__ __forceinline__ void load_chunk(const uint8_t *blk, int fmt, int i0, 
       const uint4 *p = reinterpret_cast<const uint4 *>(blk + 2 * (size_t)i0);
 #pragma unroll
       for (int q = 0; q < SPT / 8; q++) {
-        uint4 v = __ldg(p + q);
+        uint4 v = ld_in<SMEM>(p + q);
         w[4 * q + 0] = v.x;
         w[4 * q + 1] = v.y;
         w[4 * q + 2] = v.z;
@@ -119,17 +144,17 @@ __device__ __forceinline__ void load_chunk(const uint8_t *blk, int fmt, int i0, 
       const uint32_t *p = reinterpret_cast<const uint32_t *>(blk + (size_t)(i0 >> 1));
 #pragma unroll
       for (int q = 0; q < SPT / 8; q++) {
-        uint32_t v = __ldg(p + q);
-        w[4 * q + 0] = unpack_lut[v & 0xff];
-        w[4 * q + 1] = unpack_lut[(v >> 8) & 0xff];
-        w[4 * q + 2] = unpack_lut[(v >> 16) & 0xff];
-        w[4 * q + 3] = unpack_lut[v >> 24];
+        uint32_t v = ld_in<SMEM>(p + q);
+        w[4 * q + 0] = unpack_byte(v & 0xff);
+        w[4 * q + 1] = unpack_byte((v >> 8) & 0xff);
+        w[4 * q + 2] = unpack_byte((v >> 16) & 0xff);
+        w[4 * q + 3] = unpack_byte(v >> 24);
       }
     } else {
       const uint32_t *p = reinterpret_cast<const uint32_t *>(blk + (size_t)i0);
 #pragma unroll
       for (int q = 0; q < SPT / 4; q++) {
-        uint32_t v = __ldg(p + q);
+        uint32_t v = ld_in<SMEM>(p + q);
         w[2 * q + 0] = __byte_perm(v, 0, 0x4140);  // (I0,0,I1,0)
         w[2 * q + 1] = __byte_perm(v, 0, 0x4342);
       }
@@ -152,33 +177,79 @@ __device__ __forceinline__ void load_chunk(const uint8_t *blk, int fmt, int i0, 
   }
 }
 
-// The per-thread hot loop: SPT samples, running NCOs, packed I/Q MACs.
+// ---- TMA / mbarrier helpers (sm_90+ PTX) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// The per-thread hot loop: SPT samples in groups of four.  Requires 1 <= kinc and 4*kinc < 2^32
+// (checked by prepare_block), so at most one code-NCO carry falls inside a group: samples before it
+// use the current E/P/L bits, samples after it the next table entry (correlator.c:227-250).
 template <int SPT>
 __device__ __forceinline__ void correlate_chunk(const uint32_t (&w)[SPT / 2], uint32_t cph, uint32_t kph,
                                                 const uint32_t cinc, const uint32_t kinc, const uint32_t *tbl,
                                                 uint32_t h, uint32_t bits, const uint2 *lut, int &accE, int &accP,
                                                 int &accL) {
-  int cE = sext8(bits, 0), cP = sext8(bits, 1), cL = sext8(bits, 2);
+  int oE = sext8(bits, 0), oP = sext8(bits, 1), oL = sext8(bits, 2);
   int aE = 0, aP = 0, aL = 0;
+  uint32_t hp = smem_u32(tbl + h);
+  const uint32_t t1 = 0u - kinc, t2 = 0u - 2u * kinc, t3 = 0u - 3u * kinc, k4 = 4u * kinc;
 #pragma unroll
-  for (int j = 0; j < SPT; j++) {
-    const uint32_t word = w[j >> 1];
-    const int I = sext8(word, (j & 1) * 2), Q = sext8(word, (j & 1) * 2 + 1);
-    const uint2 ab = lut[cph >> 29];
-    const int v = I * (int)ab.x + Q * (int)ab.y;  // ival + 65536*qval
-    aE += cE * v;
-    aP += cP * v;
-    aL += cL * v;
-    cph += cinc;
-    const uint32_t k2 = kph + kinc;
-    if (k2 < kph) {  // code NCO carry: next half chip (correlator.c:246-250)
-      h++;
-      const uint32_t t = tbl[h];
-      cE = sext8(t, 0);
-      cP = sext8(t, 1);
-      cL = sext8(t, 2);
+  for (int g8 = 0; g8 < SPT / 8; g8++) {
+    // eight LO look-ups in flight before the first product (shared-memory latency ~30 cycles)
+    uint2 ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      ab[j] = lut[cph >> 29];
+      cph += cinc;
     }
-    kph = k2;
+    int v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t word = w[(8 * g8 + j) >> 1];
+      const int I = sext8(word, (j & 1) * 2), Q = sext8(word, (j & 1) * 2 + 1);
+      v[j] = I * (int)ab[j].x + Q * (int)ab[j].y;  // ival + 65536*qval
+    }
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      // sample j >= 1 still sees the old bits iff no carry happened in samples 0..j-1: kph + j*kinc < 2^32
+      const bool m1 = kph < t1, m2 = kph < t2, m3 = kph < t3;
+      int so = v[4 * g], sn = 0;
+      if (m1) so += v[4 * g + 1]; else sn += v[4 * g + 1];
+      if (m2) so += v[4 * g + 2]; else sn += v[4 * g + 2];
+      if (m3) so += v[4 * g + 3]; else sn += v[4 * g + 3];
+      uint32_t carry;
+      asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(kph), "=r"(carry) : "r"(k4));
+      hp += carry << 2;
+      uint32_t t;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(hp));
+      const int nE = sext8(t, 0), nP = sext8(t, 1), nL = sext8(t, 2);
+      aE += oE * so + nE * sn;
+      aP += oP * so + nP * sn;
+      aL += oL * so + nL * sn;
+      oE = nE;
+      oP = nP;
+      oL = nL;
+    }
   }
   accE = aE;
   accP = aP;
@@ -201,7 +272,7 @@ struct ChanShared {
   int dump_count;
 };
 
-__device__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+__device__ __forceinline__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
   const long long n = a.nsamp;
   if (cs.tic < n) {  // correlator.c:155-165
     sp.tic_count = (int)cs.tic;
@@ -210,6 +281,8 @@ __device__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a
     cs.tic -= n;
     sp.tic_count = -1;
   }
+  sp.tic = cs.tic;
+  sp.cyc_pending = 0;
   ChRegs &r = cs.r;
   gnssb200_corr &g = cs.g;
   if (r.w_epoch != -1) {  // :177-182
@@ -235,7 +308,7 @@ __device__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a
   sp.stale_idx = (uint32_t)(sp.hc0 + w1);
   bool fast = (r.w_prn == tbl_prn) && r.w_prn >= 1 && r.w_prn <= 32 && slew_dump >= 1 && slew_dump < 65536 &&
               (long long)wtot < w1 + slew_dump && (sp.hc0 + wtot + 40) < SMEM_TBL && (sp.hc0 + w1) < SMEM_TBL &&
-              n < (1ll << 30);
+              n < (1ll << 30) && sp.kinc >= 1u && sp.kinc < (1u << 30);
   sp.mode = fast ? MODE_FAST : MODE_SERIAL;
 }
 
@@ -249,7 +322,7 @@ __device__ __forceinline__ void apply_dump_counters(ChanShared &cs) {
   cs.r.r_meas[7] = g.ms_counter + (g.bit_counter << 8);
 }
 
-__device__ void finalize_fast(ChanShared &cs, const StepParams &sp, const int (&A)[6], const int (&B)[6], int nsamp) {
+__device__ __forceinline__ void finalize_fast(ChanShared &cs, const StepParams &sp, const int (&A)[6], const int (&B)[6], int nsamp) {
   gnssb200_corr &g = cs.g;
   ChRegs &r = cs.r;
   const unsigned long long n = (unsigned long long)nsamp;
@@ -295,7 +368,8 @@ __device__ void finalize_fast(ChanShared &cs, const StepParams &sp, const int (&
 }
 
 // literal per-sample walk of one block by a single lane (any register contents)
-__device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, const TrackArgs &a, const uint8_t *blk) {
+__device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, const uint32_t *code_table, int fmt, int nsamp,
+                                          const uint8_t *blk) {
   const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
   const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
   gnssb200_corr &g = cs.g;
@@ -305,15 +379,15 @@ __device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, 
   uint16_t hc = (uint16_t)g.half_chip;
   auto bits_at = [&](uint16_t hh) -> uint32_t {
     long long f = row + hh;
-    return (f >= 0 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+    return (f >= 0 && f < TABLE_ENTRIES) ? code_table[f] : 0u;
   };
   uint32_t t = bits_at(hc);
   int cE = sext8(t, 0), cP = sext8(t, 1), cL = sext8(t, 2);
   int dumped = 0;
-  for (int i = 0; i < a.nsamp; i++) {
+  for (int i = 0; i < nsamp; i++) {
     const int k = g.carrier_phase >> 29;
     int I, Q;
-    load_sample(blk, a.fmt, i, I, Q);
+    load_sample(blk, fmt, i, I, Q);
     const int vq = q_lo[k] * I - i_lo[k] * Q;
     const int vi = i_lo[k] * I + q_lo[k] * Q;
     g.acc[0] += cL * vi;
@@ -357,7 +431,7 @@ __device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, 
   cs.dumped_last = dumped;
 }
 
-__device__ void after_block(ChanShared &cs, const TrackArgs &a, int s, int ch, long long block_index) {
+__device__ __forceinline__ void after_block(ChanShared &cs, const TrackArgs &a, int s, int ch, long long block_index) {
   if (!cs.dumped_last) return;
   if (a.run_isr) {
     if (dev_gpsisr_channel(cs.k, cs.r, a.cfg)) {
@@ -366,30 +440,53 @@ __device__ void after_block(ChanShared &cs, const TrackArgs &a, int s, int ch, l
     }
   }
   if (a.dumps && cs.dump_count < a.dump_cap) {
-    gnssb200_dump d;
-    d.block = (int32_t)block_index;
-    d.ch = (int16_t)ch;
-    d.state = (int16_t)cs.k.state;
-#pragma unroll
-    for (int q = 0; q < 6; q++) d.acc[q] = cs.r.r_acc[q];
-    d.carrier_incr = (uint32_t)((cs.r.w_carr_hi << 16) + cs.r.w_carr_lo);
-    d.code_incr = (uint32_t)((cs.r.w_code_hi << 16) + cs.r.w_code_lo);
-    d.n_freq = (int16_t)cs.k.n_freq;
-    d.codes = (int16_t)cs.k.codes;
-    d.slew = cs.r.w_slew;
-    a.dumps[((size_t)s * NCH + ch) * a.dump_cap + cs.dump_count] = d;
+    // 48-byte record written as three 16-byte stores
+    gnssb200_dump *out = &a.dumps[((size_t)s * NCH + ch) * a.dump_cap + cs.dump_count];
+    int4 q0, q1, q2;
+    q0.x = (int)block_index;
+    q0.y = (int)(uint16_t)(int16_t)ch | ((int)(uint16_t)(int16_t)cs.k.state << 16);
+    q0.z = cs.r.r_acc[0];
+    q0.w = cs.r.r_acc[1];
+    q1.x = cs.r.r_acc[2];
+    q1.y = cs.r.r_acc[3];
+    q1.z = cs.r.r_acc[4];
+    q1.w = cs.r.r_acc[5];
+    q2.x = (cs.r.w_carr_hi << 16) + cs.r.w_carr_lo;
+    q2.y = (cs.r.w_code_hi << 16) + cs.r.w_code_lo;
+    q2.z = (int)(uint16_t)(int16_t)cs.k.n_freq | ((int)(uint16_t)(int16_t)cs.k.codes << 16);
+    q2.w = cs.r.w_slew;
+    int4 *o4 = reinterpret_cast<int4 *>(out);
+    o4[0] = q0;
+    o4[1] = q1;
+    o4[2] = q2;
     cs.dump_count++;
   }
 }
 
-template <int SPT>
-__global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const TrackArgs a) {
+// sum over the warp of six ints (butterfly); result valid in every lane
+__device__ __forceinline__ void warp_sum6(int (&v)[6]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+}
+
+#define SPT 32
+// dynamic shared memory: two sample tiles of tile_bytes each (TMA mode only)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs a, const int use_tma, const int tile_bytes) {
   __shared__ ChanShared cs;
   __shared__ StepParams sp_s;
   __shared__ uint2 lut[8];
   __shared__ uint32_t tbl[SMEM_TBL];
+  // copy of tbl[0..47] whose entry 0 holds the bits left over from the dump (rule A6): a chunk that
+  // starts in the first post-dump half chip walks alias_tbl[0] -> tbl[1] -> tbl[2] ... like the reference
+  __shared__ uint32_t alias_tbl[48];
   __shared__ uint32_t unpack_lut[256];
-  __shared__ int partial[32][12];
+  __shared__ __align__(16) int partial[12][32];  // [value][warp]
+  __shared__ __align__(8) uint64_t mbar[2];
+  extern __shared__ __align__(128) uint8_t tiles[];
 
   const int s = a.first_stream + blockIdx.x / NCH, ch = blockIdx.x % NCH;
   gnssb200_rx *rx = a.rx + s;
@@ -397,9 +494,14 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
   const int tbl_prn = rx->reg_write[ch << 3];
 
   fill_lo_lut(lut);
+  for (int i = tid; i < 12 * 32; i += blockDim.x) (&partial[0][0])[i] = 0;
   for (int i = tid; i < SMEM_TBL; i += blockDim.x) {
     long long f = (long long)tbl_prn * HALF_CHIPS + i;
     tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+  }
+  if (tid < 48) {
+    long long f = (long long)tbl_prn * HALF_CHIPS + tid;
+    alias_tbl[tid] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   for (int i = tid; i < 256; i += blockDim.x) {
     const int val[4] = {1, -1, 3, -3};
@@ -408,6 +510,9 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
     for (int e = 0; e < 4; e++) wv |= (uint32_t)(val[(i >> (2 * e)) & 3] & 0xff) << (8 * e);
     unpack_lut[i] = wv;
   }
+  const size_t blk_bytes = bytes_for(a.fmt, a.nsamp);
+  const uint8_t *stream_base = a.d_if + (size_t)s * a.stride;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(stream_base) | blk_bytes) & 15) == 0 && (a.nsamp % 8) == 0;
   if (tid == 0) {
     cs.k = rx->chan[ch];
     cs.g = rx->corr[ch];
@@ -429,37 +534,109 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
       prepare_block(cs, sp_s, a, tbl_prn);
     else
       sp_s.mode = MODE_STOP;
+    sp_s.stale_bits = 0;
+    if (sp_s.mode == MODE_FAST) {
+      const long long f = (long long)tbl_prn * HALF_CHIPS + sp_s.stale_idx;
+      sp_s.stale_bits = f < TABLE_ENTRIES ? a.code_table[f] : 0u;
+    }
+    alias_tbl[0] = sp_s.stale_bits;
+    if (use_tma) {
+      mbar_init(&mbar[0], 1);
+      mbar_init(&mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (sp_s.mode != MODE_STOP && sp_s.mode != MODE_IDLE) {  // block 0 -> tile 0
+        mbar_expect_tx(&mbar[0], (uint32_t)blk_bytes);
+        tma_load_1d(tiles, stream_base, (uint32_t)blk_bytes, &mbar[0]);
+      }
+    }
   }
   __syncthreads();
-
-  const size_t blk_bytes = bytes_for(a.fmt, a.nsamp);
-  const uint8_t *stream_base = a.d_if + (size_t)s * a.stride;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(stream_base) | blk_bytes) & 15) == 0 && (a.nsamp % 8) == 0;
   const long long first_block = rx->blocks_done;
-
-  uint32_t cur[SPT / 2], nxt[SPT / 2];
   const int my_i0 = tid * SPT;
-  if (sp_s.mode != MODE_STOP && my_i0 < a.nsamp) load_chunk<SPT>(stream_base, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, cur);
 
 #ifdef TRACK_PROFILE
-  long long t_main = 0, t_red = 0, t_isr = 0, t_sync2 = 0, t_corr = 0;
+  long long t_main = 0, t_red = 0, t_isr = 0, t_sync2 = 0, t_corr = 0, t_quiet = 0, n_quiet = 0, t_fin = 0, t_after = 0, t_prep = 0, t_wait = 0, t_head = 0, t_load = 0, t_setup = 0, t_post = 0;
+  long long t_state[8] = {0,0,0,0,0,0,0,0}, n_state[8] = {0,0,0,0,0,0,0,0};
 #endif
+  // Every thread keeps a (uniform) copy of the block parameters.  A block without dump, TIC latch or
+  // mode change is "quiet": nothing leaves the thread -- its sums are carried in registers, the
+  // parameters of the next block follow from the closed forms, and neither the reduction nor the
+  // ISR lane runs.  Only blocks with an event (a dump, about every second block) synchronise.
+  StepParams sp = sp_s;
+  int carry[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long nk = (unsigned long long)a.nsamp * sp.kinc, nc = (unsigned long long)a.nsamp * sp.cinc;
   for (long long b = 0; b < a.nblocks; b++) {
 #ifdef TRACK_PROFILE
     long long c0 = clock64();
 #endif
-    const StepParams sp = sp_s;
     if (sp.mode == MODE_STOP) break;
     const uint8_t *blk = stream_base + (size_t)b * blk_bytes;
     int sumA[6] = {0, 0, 0, 0, 0, 0}, sumB[6] = {0, 0, 0, 0, 0, 0};
     bool anyB = false;
+    // parameters the next block would have if this one is quiet
+    StepParams nx = sp;
+    bool quiet = false;
+    if (sp.mode == MODE_FAST && b + 1 < a.nblocks) {
+      const unsigned long long n = (unsigned long long)a.nsamp;
+      const unsigned long long kend = (unsigned long long)sp.kph0 + nk;
+      const unsigned long long cend = (unsigned long long)sp.cph0 + nc;
+      const uint32_t wtot = (uint32_t)(kend >> 32);
+      nx.kph0 = (uint32_t)kend;
+      nx.cph0 = (uint32_t)cend;
+      nx.hc0 = sp.hc0 + wtot;
+      nx.w1 = sp.w1 - wtot;
+      nx.cyc_pending = sp.cyc_pending + (uint32_t)(cend >> 32);
+      if (sp.tic < (long long)n) {
+        nx.tic_count = (int)sp.tic;
+        nx.tic = sp.tic + a.cfg.tic_ref - (long long)n;
+      } else {
+        nx.tic_count = -1;
+        nx.tic = sp.tic - (long long)n;
+      }
+      const unsigned long long wnext = ((unsigned long long)nx.kph0 + nk) >> 32;
+      const bool next_fast = wnext < (unsigned long long)nx.w1 + sp.slew_dump && (nx.hc0 + wnext + 40) < SMEM_TBL;
+      quiet = wtot < sp.w1 && !(sp.tic_count >= 0 && sp.tic_count < a.nsamp) && next_fast;
+    }
+    const uint8_t *tile = tiles + (size_t)(b & 1) * tile_bytes;
+
+    if (use_tma && sp.mode != MODE_IDLE) {
+      // prefetch block b+1 into the other tile (every thread finished reading it before the barrier
+      // that ended block b-1), then wait for block b
+      if (tid == 0 && b + 1 < a.nblocks) {
+        mbar_expect_tx(&mbar[(b + 1) & 1], (uint32_t)blk_bytes);
+        tma_load_1d(tiles + (size_t)((b + 1) & 1) * tile_bytes, blk + blk_bytes, (uint32_t)blk_bytes, &mbar[(b + 1) & 1]);
+      }
+#ifdef TRACK_PROFILE
+      long long w0c = clock64();
+#endif
+      mbar_wait(&mbar[b & 1], (uint32_t)((b >> 1) & 1));
+#ifdef TRACK_PROFILE
+      t_wait += clock64() - w0c;
+#endif
+    }
+#ifdef TRACK_PROFILE
+    t_head += clock64() - c0;
+#endif
 
     if (sp.mode == MODE_FAST) {
       // trip count is uniform over the CTA (warp collectives inside); `live` masks ragged tails
-      for (int base = 0, tile = 0; base < a.nsamp; base += blockDim.x * SPT, tile++) {
+      for (int base = 0; base < a.nsamp; base += blockDim.x * SPT) {
         const int i0 = base + my_i0;
         const bool live = i0 < a.nsamp;
-        if (tile > 0 && live) load_chunk<SPT>(blk, a.fmt, i0, a.nsamp, aligned, unpack_lut, cur);
+        uint32_t cur[SPT / 2];
+#ifdef TRACK_PROFILE
+        long long l0c = clock64();
+#endif
+        if (live) {
+          if (use_tma)
+            load_chunk<SPT, true>(tile, a.fmt, i0, a.nsamp, true, unpack_lut, cur);  // shared-memory tile
+          else
+            load_chunk<SPT>(blk, a.fmt, i0, a.nsamp, aligned, unpack_lut, cur);
+        }
+#ifdef TRACK_PROFILE
+        t_load += clock64() - l0c + (cur[0] & 0);
+#endif
         const int i1 = live ? min(i0 + SPT, a.nsamp) : i0 + 1;
         const unsigned long long k0 = (unsigned long long)sp.kph0 + (unsigned long long)i0 * sp.kinc;
         const uint32_t w_start = (uint32_t)(k0 >> 32);
@@ -477,11 +654,15 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
 #ifdef TRACK_PROFILE
         long long cc0 = clock64();
 #endif
+        // chunk starting in the first post-dump half chip: stale bits first, then tbl[1], tbl[2], ...
+        const bool stale_start = allB && h == 0;
         if (live)
-          correlate_chunk<SPT>(cur, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc, tbl, h, tbl[hl],
-                               lut, pE, pP, pL);
+          correlate_chunk<SPT>(cur, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc,
+                               stale_start ? alias_tbl : tbl, h, stale_start ? sp.stale_bits : tbl[hl], lut, pE, pP, pL);
 #ifdef TRACK_PROFILE
         t_corr += clock64() - cc0 + (pE & 0);
+        t_setup += cc0 - l0c;
+        long long p0c = clock64();
 #endif
         const bool straddle = !allA && !allB;
         if (!straddle && live) {
@@ -511,7 +692,7 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
             const uint32_t hh = inA ? sp.hc0 + wb : (rel == 0 ? sp.stale_idx : rel);
             const uint32_t t = tbl[hh];
             int I, Q;
-            load_sample(blk, a.fmt, i, I, Q);
+            load_sample(use_tma ? tile : blk, a.fmt, i, I, Q);
             const uint2 ab = lut[(sp.cph0 + (uint32_t)i * sp.cinc) >> 29];
             const int v = I * (int)ab.x + Q * (int)ab.y;
             int vi, vq;
@@ -527,27 +708,42 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
           }
         }
         anyB |= !allA;
-      }
-#ifdef TRACK_DEBUG
-      if (ch == 0 && b < 2 && (tid < 3 || tid == 255))
-        printf("  tid=%d b=%lld sumA=%d %d %d %d %d %d cur0=%08x\n", tid, b, sumA[0], sumA[1], sumA[2], sumA[3], sumA[4], sumA[5], cur[0]);
+#ifdef TRACK_PROFILE
+        t_post += clock64() - p0c;
 #endif
-      // prefetch this thread's first chunk of the next block while the reduction / ISR runs
-      if (b + 1 < a.nblocks && my_i0 < a.nsamp)
-        load_chunk<SPT>(blk + blk_bytes, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, nxt);
-      // warp reduction
-      const bool warpB = __any_sync(0xffffffffu, anyB);
+      }
+      if (quiet) {  // no dump in this block: every chunk was pre-dump, keep the sums in registers
+#pragma unroll
+        for (int q = 0; q < 6; q++) carry[q] += sumA[q];
+        sp = nx;
+        __syncthreads();  // tile (b+1)&1 may be refilled by the TMA issue of the next iteration
+#ifdef TRACK_PROFILE
+        t_quiet += clock64() - c0;
+        n_quiet++;
+#endif
+        continue;
+      }
 #pragma unroll
       for (int q = 0; q < 6; q++) {
-        int ra = __reduce_add_sync(0xffffffffu, sumA[q]);
-        int rb = warpB ? __reduce_add_sync(0xffffffffu, sumB[q]) : 0;
-        if (lane == 0) {
-          partial[warp][q] = ra;
-          partial[warp][6 + q] = rb;
-        }
+        sumA[q] += carry[q];
+        carry[q] = 0;
       }
-    } else if (b + 1 < a.nblocks && my_i0 < a.nsamp) {
-      load_chunk<SPT>(blk + blk_bytes, a.fmt, my_i0, a.nsamp, aligned, unpack_lut, nxt);
+      // warp reduction (shuffles); the post-dump set only where a warp has post-dump samples
+      const bool warpB = __any_sync(0xffffffffu, anyB);
+      warp_sum6(sumA);
+      if (warpB) warp_sum6(sumB);
+      if (lane < 6) {
+        int va = sumA[0], vb = sumB[0];
+#pragma unroll
+        for (int q = 1; q < 6; q++) {
+          if (lane == q) {
+            va = sumA[q];
+            vb = sumB[q];
+          }
+        }
+        partial[lane][warp] = va;
+        partial[6 + lane][warp] = warpB ? vb : 0;
+      }
     }
 #ifdef TRACK_PROFILE
     long long c1 = clock64();
@@ -560,38 +756,62 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
     if (warp == 0) {
       int A[6], B[6];
       if (sp.mode == MODE_FAST) {
+        // lanes 0..11 each add one value over the warps (two 16-byte loads), then lane 0 collects
+        int tot = 0;
+        if (lane < 12) {
+          for (int w4 = 0; w4 < nwarps; w4 += 4) {
+            const int4 p4 = *reinterpret_cast<const int4 *>(&partial[lane][w4]);
+            tot += p4.x + p4.y + p4.z + p4.w;  // rows are zero beyond nwarps
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 6; q++) {
-          A[q] = __reduce_add_sync(0xffffffffu, lane < nwarps ? partial[lane][q] : 0);
-          B[q] = __reduce_add_sync(0xffffffffu, lane < nwarps ? partial[lane][6 + q] : 0);
+          A[q] = __shfl_sync(0xffffffffu, tot, q);
+          B[q] = __shfl_sync(0xffffffffu, tot, 6 + q);
         }
       }
       if (tid == 0) {
-#ifdef TRACK_DEBUG
-        if (ch == 0 && b < 4)
-          printf("b=%lld mode=%d cph0=%u kph0=%u cinc=%u kinc=%u hc0=%u w1=%u stale=%u A=%d %d %d %d %d %d B=%d %d %d %d %d %d\n", b,
-                 sp.mode, sp.cph0, sp.kph0, sp.cinc, sp.kinc, sp.hc0, sp.w1, sp.stale_idx, A[0], A[1], A[2], A[3], A[4], A[5],
-                 B[0], B[1], B[2], B[3], B[4], B[5]);
+        // state that advanced in registers during quiet blocks
+#ifdef TRACK_PROFILE
+        long long i0c = clock64();
 #endif
+        cs.tic = sp.tic;
+        cs.g.carrier_cycle += sp.cyc_pending;
         if (sp.mode == MODE_FAST)
           finalize_fast(cs, sp, A, B, a.nsamp);
         else if (sp.mode == MODE_SERIAL)
-          serial_block(cs, sp, a, blk);
+          serial_block(cs, sp, a.code_table, a.fmt, a.nsamp, use_tma ? tile : blk);
         else
           cs.dumped_last = 0;
+#ifdef TRACK_PROFILE
+        long long i1c = clock64();
+#endif
         after_block(cs, a, s, ch, first_block + b);
+#ifdef TRACK_PROFILE
+        long long i2c = clock64();
+        t_fin += i1c - i0c; t_after += i2c - i1c; t_state[cs.k.state & 7] += i2c - i1c; n_state[cs.k.state & 7]++;
+#endif
         if (cs.halted || sp.mode == MODE_IDLE)  // an idle channel has no ISR: nothing can change any more
           sp_s.mode = MODE_STOP;
-        else if (b + 1 < a.nblocks)
+        else if (b + 1 < a.nblocks) {
           prepare_block(cs, sp_s, a, tbl_prn);
+          if (sp_s.mode == MODE_FAST) {
+            sp_s.stale_bits = tbl[sp_s.stale_idx];
+            alias_tbl[0] = sp_s.stale_bits;  // other threads read it only after the barrier below
+          }
+        }
+#ifdef TRACK_PROFILE
+        t_prep += clock64() - i2c;
+#endif
       }
     }
 #ifdef TRACK_PROFILE
     long long c3 = clock64();
 #endif
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < SPT / 2; q++) cur[q] = nxt[q];
+    sp = sp_s;
+    nk = (unsigned long long)a.nsamp * sp.kinc;
+    nc = (unsigned long long)a.nsamp * sp.cinc;
 #ifdef TRACK_PROFILE
     long long c4 = clock64();
     t_main += c1 - c0; t_red += c2 - c1; t_isr += c3 - c2; t_sync2 += c4 - c3;
@@ -599,8 +819,17 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
   }
 #ifdef TRACK_PROFILE
   if (blockIdx.x == 0 && (tid == 0 || tid == 37 || tid == 255))
-    printf("tid %d: main %lld (corr %lld)  sync1 %lld  isr %lld  sync2 %lld cycles/block\n", tid, t_main / a.nblocks,
-           t_corr / a.nblocks, t_red / a.nblocks, t_isr / a.nblocks, t_sync2 / a.nblocks);
+  {
+    const long long ne = a.nblocks - n_quiet;
+    printf("tid %d: quiet blocks %lld x %lld cyc; event blocks %lld: main %lld sync1 %lld isr %lld sync2 %lld; corr/block %lld\n", tid, n_quiet,
+           n_quiet ? t_quiet / n_quiet : 0, ne, t_main / ne, t_red / ne, t_isr / ne, t_sync2 / ne, t_corr / a.nblocks);
+    printf("   tid %d: head(incl wait) %lld  mbar wait %lld  load %lld  load+setup %lld  post(unpack,straddle) %lld per block\n", tid, t_head / a.nblocks,
+           t_wait / a.nblocks, t_load / a.nblocks, t_setup / a.nblocks, t_post / a.nblocks);
+    if (tid == 0)
+      printf("   isr lane: finalize %lld  after_block %lld  prepare %lld per event; after_block by state after: acq %lld (%lld) conf %lld (%lld) pull %lld (%lld) track %lld (%lld)\n",
+             t_fin / ne, t_after / ne, t_prep / ne, n_state[1] ? t_state[1] / n_state[1] : 0, n_state[1], n_state[2] ? t_state[2] / n_state[2] : 0, n_state[2],
+             n_state[3] ? t_state[3] / n_state[3] : 0, n_state[3], n_state[4] ? t_state[4] / n_state[4] : 0, n_state[4]);
+  }
 #endif
 
   if (tid == 0) {
@@ -619,6 +848,7 @@ __global__ void __launch_bounds__(1024 / (SPT / 8)) track_loop_kernel(const Trac
     if (a.dump_count) a.dump_count[s * NCH + ch] = cs.dump_count;
   }
 }
+#undef SPT
 
 // one thread per stream: status words, TIC counter and block counter after a run
 __global__ void track_finish_kernel(gnssb200_rx *rx, const int32_t *chan_flags, int first_stream, int n_streams,
@@ -698,24 +928,45 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   a.dump_count = d_dump_count;
   a.cfg = h->cfg;
   const int grid = n_streams * NCH;
-  // threads: one tile of SPT-sample chunks covers the block when possible
-  static int forced_spt = -1;
-  if (forced_spt < 0) {
-    const char *e = getenv("GNSSB200_TRACK_SPT");
-    forced_spt = e ? atoi(e) : 0;
-  }
-  int spt = forced_spt ? forced_spt : 32;
+  const int spt = 32;
   int threads = (nsamp + spt - 1) / spt;
   threads = ((threads + 31) / 32) * 32;
-  const int max_threads = 1024 / (spt / 8);
-  if (threads > max_threads) threads = max_threads;
+  if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
-  if (spt == 32)
-    track_loop_kernel<32><<<grid, threads, 0, st>>>(a);
-  else if (spt == 16)
-    track_loop_kernel<16><<<grid, threads, 0, st>>>(a);
+  // TMA staging needs 16-byte aligned blocks that fit one tile per CTA pass
+  const size_t blk_bytes = fmt == GNSSB200_FMT_INT8_IQ ? (size_t)nsamp * 2 : (fmt == GNSSB200_FMT_PACKED2 ? (size_t)nsamp / 2 : (size_t)nsamp);
+  const bool aligned = (((uintptr_t)d_if | stride | blk_bytes) & 15) == 0 && (nsamp % 8) == 0;
+  static int no_tma = -1;
+  if (no_tma < 0) {
+    const char *e = getenv("GNSSB200_TRACK_NO_TMA");
+    no_tma = (e && atoi(e)) ? 1 : 0;
+  }
+  const int use_tma = (aligned && !no_tma && nsamp <= threads * spt && blk_bytes <= 65536) ? 1 : 0;
+  const int tile_bytes = use_tma ? (int)((blk_bytes + 127) & ~(size_t)127) : 0;
+  const size_t dyn = (size_t)2 * tile_bytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 256));
+    attr_done = true;
+  }
+  // few channels per SM: 128 registers buy instruction-level parallelism for the shared-memory look-ups;
+  // many channels per SM: 64 registers, four resident CTAs hide the same latencies with other channels' warps
+  static int force_occ = -1;
+  if (force_occ < 0) {
+    const char *e = getenv("GNSSB200_TRACK_OCC");
+    force_occ = e ? atoi(e) : 0;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const bool dense = force_occ ? (force_occ >= 4) : (grid > 3 * sms);
+  if (threads <= 256 && dense)
+    track_loop_kernel<256, 4><<<grid, threads, dyn, st>>>(a, use_tma, tile_bytes);
+  else if (threads <= 256)
+    track_loop_kernel<256, 2><<<grid, threads, dyn, st>>>(a, use_tma, tile_bytes);
   else
-    track_loop_kernel<8><<<grid, threads, 0, st>>>(a);
+    track_loop_kernel<1024, 1><<<grid, threads, dyn, st>>>(a, use_tma, tile_bytes);
   CUDA_TRY(cudaGetLastError());
   track_finish_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(h->d_rx, h->d_chan_flags, first_stream, n_streams, nsamp,
                                                                nblocks, h->cfg.tic_ref);

@@ -315,6 +315,8 @@ static unsigned isqrt_newton(int64_t L) {
   }
 }
 
+unsigned orc_isqrt(long L) { return isqrt_newton((int64_t)L); }
+
 static int64_t atan2_fix(int64_t y, int64_t x) { /* 1 rad = 16384 */
   const int64_t half_pi = 25736, pi = 51472;
   int64_t n, n3, res = 0;
@@ -341,6 +343,8 @@ static int64_t atan2_fix(int64_t y, int64_t x) { /* 1 rad = 16384 */
   }
   return res;
 }
+
+long orc_atan2(long y, long x) { return (long)atan2_fix((int64_t)y, (int64_t)x); }
 
 static inline int sgn(int64_t v) { return v > 0 ? 1 : (v == 0 ? 0 : -1); }
 
