@@ -358,6 +358,8 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu:
         cpu, parity = cpu_baseline(args, d_if, fmt, scs[0], h_dumps, h_cnt, nblk)
 
+    torch.cuda.synchronize()
+    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -439,7 +441,8 @@ def bench_acquisition(eng, dev, rank, world, clocks):
         found = sorted(int(r.sv) for r in res if r.sv != 0 or (st.system == "glonass" and r.peakMetric > st.acqThreshold))
         cells = n_sv * nb * N
         G = n_sv * nb
-        flops = fl["B"] * fl["K"] * (nb * (8 * fl["T"] * N + 5 * N * np.log2(N)) + G * (6 * N + 5 * N * np.log2(N) + 3 * N))
+        n_base = G if st.system == "glonass" else nb  # C3 counts one forward spectrum per (FCH, bin)
+        flops = fl["B"] * fl["K"] * (n_base * (8 * fl["T"] * N + 5 * N * np.log2(N)) + G * (6 * N + 5 * N * np.log2(N) + 3 * N))
         tt = float(t.item())
         out[name] = {"cells": cells, "cells_per_s": cells / tt, "ms": tt * 1e3, "kernel_ms_rank0": ae.last_kernel_ms(),
                      "algorithmic_gflop": flops / 1e9, "fp32_tflops_achieved": flops / tt / 1e12,

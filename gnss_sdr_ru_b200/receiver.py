@@ -88,6 +88,10 @@ class TrackingEngine:
             self.h = None
 
     def __del__(self):
+        import sys
+
+        if sys.is_finalizing():  # CUDA may already be torn down at interpreter exit
+            return
         try:
             self.close()
         except Exception:
