@@ -474,8 +474,12 @@ __device__ __forceinline__ void warp_sum6(int (&v)[6]) {
 
 #define SPT 32
 // dynamic shared memory: two sample tiles of tile_bytes each (TMA mode only)
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs a, const int use_tma, const int tile_bytes) {
+// FMT >= 0 fixes the sample format at compile time (the TMA-staged hot variants); FMT < 0 reads it from
+// the arguments (generic variant: unaligned / ragged / I-only blocks, loaded straight from global memory).
+template <int MAXT, int MINB, int FMT, bool TMA>
+__global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs a, const int tile_bytes) {
+  constexpr bool use_tma = TMA;
+  const int fmt = FMT >= 0 ? FMT : a.fmt;
   __shared__ ChanShared cs;
   __shared__ StepParams sp_s;
   __shared__ uint2 lut[8];
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
     for (int e = 0; e < 4; e++) wv |= (uint32_t)(val[(i >> (2 * e)) & 3] & 0xff) << (8 * e);
     unpack_lut[i] = wv;
   }
-  const size_t blk_bytes = bytes_for(a.fmt, a.nsamp);
+  const size_t blk_bytes = bytes_for(fmt, a.nsamp);
   const uint8_t *stream_base = a.d_if + (size_t)s * a.stride;
   const bool aligned = ((reinterpret_cast<uintptr_t>(stream_base) | blk_bytes) & 15) == 0 && (a.nsamp % 8) == 0;
   if (tid == 0) {
@@ -630,9 +634,9 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
 #endif
         if (live) {
           if (use_tma)
-            load_chunk<SPT, true>(tile, a.fmt, i0, a.nsamp, true, unpack_lut, cur);  // shared-memory tile
+            load_chunk<SPT, true>(tile, fmt, i0, a.nsamp, true, unpack_lut, cur);  // shared-memory tile
           else
-            load_chunk<SPT>(blk, a.fmt, i0, a.nsamp, aligned, unpack_lut, cur);
+            load_chunk<SPT>(blk, fmt, i0, a.nsamp, aligned, unpack_lut, cur);
         }
 #ifdef TRACK_PROFILE
         t_load += clock64() - l0c + (cur[0] & 0);
@@ -692,7 +696,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
             const uint32_t hh = inA ? sp.hc0 + wb : (rel == 0 ? sp.stale_idx : rel);
             const uint32_t t = tbl[hh];
             int I, Q;
-            load_sample(use_tma ? tile : blk, a.fmt, i, I, Q);
+            load_sample(use_tma ? tile : blk, fmt, i, I, Q);
             const uint2 ab = lut[(sp.cph0 + (uint32_t)i * sp.cinc) >> 29];
             const int v = I * (int)ab.x + Q * (int)ab.y;
             int vi, vq;
@@ -780,7 +784,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
         if (sp.mode == MODE_FAST)
           finalize_fast(cs, sp, A, B, a.nsamp);
         else if (sp.mode == MODE_SERIAL)
-          serial_block(cs, sp, a.code_table, a.fmt, a.nsamp, use_tma ? tile : blk);
+          serial_block(cs, sp, a.code_table, fmt, a.nsamp, use_tma ? tile : blk);
         else
           cs.dumped_last = 0;
 #ifdef TRACK_PROFILE
@@ -941,14 +945,15 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     const char *e = getenv("GNSSB200_TRACK_NO_TMA");
     no_tma = (e && atoi(e)) ? 1 : 0;
   }
-  const int use_tma = (aligned && !no_tma && nsamp <= threads * spt && blk_bytes <= 65536) ? 1 : 0;
+  const int use_tma = (aligned && !no_tma && nsamp <= 256 * spt && blk_bytes <= 16384) ? 1 : 0;
   const int tile_bytes = use_tma ? (int)((blk_bytes + 127) & ~(size_t)127) : 0;
   const size_t dyn = (size_t)2 * tile_bytes;
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
     attr_done = true;
   }
   // few channels per SM: 128 registers buy instruction-level parallelism for the shared-memory look-ups;
@@ -961,12 +966,17 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const bool dense = force_occ ? (force_occ >= 4) : (grid > 3 * sms);
-  if (threads <= 256 && dense)
-    track_loop_kernel<256, 4><<<grid, threads, dyn, st>>>(a, use_tma, tile_bytes);
-  else if (threads <= 256)
-    track_loop_kernel<256, 2><<<grid, threads, dyn, st>>>(a, use_tma, tile_bytes);
+  const bool hot = use_tma && threads <= 256 && (fmt == GNSSB200_FMT_INT8_IQ || fmt == GNSSB200_FMT_PACKED2);
+  if (hot && fmt == GNSSB200_FMT_INT8_IQ && dense)
+    track_loop_kernel<256, 4, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
+  else if (hot && fmt == GNSSB200_FMT_INT8_IQ)
+    track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
+  else if (hot && dense)
+    track_loop_kernel<256, 4, GNSSB200_FMT_PACKED2, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
+  else if (hot)
+    track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
   else
-    track_loop_kernel<1024, 1><<<grid, threads, dyn, st>>>(a, use_tma, tile_bytes);
+    track_loop_kernel<1024, 1, -1, false><<<grid, threads, 0, st>>>(a, 0);
   CUDA_TRY(cudaGetLastError());
   track_finish_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(h->d_rx, h->d_chan_flags, first_stream, n_streams, nsamp,
                                                                nblocks, h->cfg.tic_ref);
