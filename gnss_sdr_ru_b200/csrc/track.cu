@@ -22,7 +22,7 @@
 //   dump:       at most one per block on this path; a chunk lies before, after or across it.  The
 //               (single) straddling chunk is re-evaluated sample-per-lane by its warp with the
 //               closed forms, so no thread carries two accumulator sets through its loop.
-//   reduce:     warp shuffles, then 12 x 8 partials through shared memory.
+//   reduce:     warp shuffles, then twelve shared-memory atomics per warp.
 //   ISR:        lane 0 of warp 0 applies the dump / TIC / epoch rules, runs the channel state
 //               machine (isr_device.cuh) and publishes next block's NCO words.
 //
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   // starts in the first post-dump half chip walks alias_tbl[0] -> tbl[1] -> tbl[2] ... like the reference
   __shared__ uint32_t alias_tbl[48];
   __shared__ uint32_t unpack_lut[256];
-  __shared__ __align__(16) int partial[12][32];  // [value][warp]
+  __shared__ __align__(16) int totals[12];  // six pre-dump and six post-dump sums, accumulated by shared-memory atomics
   __shared__ __align__(8) uint64_t mbar[2];
   extern __shared__ __align__(128) uint8_t tiles[];
 
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   const int tbl_prn = rx->reg_write[ch << 3];
 
   fill_lo_lut(lut);
-  for (int i = tid; i < 12 * 32; i += blockDim.x) (&partial[0][0])[i] = 0;
+  if (tid < 12) totals[tid] = 0;
   for (int i = tid; i < SMEM_TBL; i += blockDim.x) {
     long long f = (long long)tbl_prn * HALF_CHIPS + i;
     tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
@@ -745,8 +745,8 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
             vb = sumB[q];
           }
         }
-        partial[lane][warp] = va;
-        partial[6 + lane][warp] = warpB ? vb : 0;
+        atomicAdd(&totals[lane], va);
+        if (warpB) atomicAdd(&totals[6 + lane], vb);
       }
     }
 #ifdef TRACK_PROFILE
@@ -759,20 +759,16 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
 
     if (warp == 0) {
       int A[6], B[6];
-      if (sp.mode == MODE_FAST) {
-        // lanes 0..11 each add one value over the warps (two 16-byte loads), then lane 0 collects
-        int tot = 0;
-        if (lane < 12) {
-          for (int w4 = 0; w4 < nwarps; w4 += 4) {
-            const int4 p4 = *reinterpret_cast<const int4 *>(&partial[lane][w4]);
-            tot += p4.x + p4.y + p4.z + p4.w;  // rows are zero beyond nwarps
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-          A[q] = __shfl_sync(0xffffffffu, tot, q);
-          B[q] = __shfl_sync(0xffffffffu, tot, 6 + q);
-        }
+      if (sp.mode == MODE_FAST && tid == 0) {
+        const int4 t0 = *reinterpret_cast<const int4 *>(&totals[0]);
+        const int4 t1 = *reinterpret_cast<const int4 *>(&totals[4]);
+        const int4 t2 = *reinterpret_cast<const int4 *>(&totals[8]);
+        A[0] = t0.x; A[1] = t0.y; A[2] = t0.z; A[3] = t0.w; A[4] = t1.x; A[5] = t1.y;
+        B[0] = t1.z; B[1] = t1.w; B[2] = t2.x; B[3] = t2.y; B[4] = t2.z; B[5] = t2.w;
+        const int4 z = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<int4 *>(&totals[0]) = z;  // ready for the next event (barrier below orders it)
+        *reinterpret_cast<int4 *>(&totals[4]) = z;
+        *reinterpret_cast<int4 *>(&totals[8]) = z;
       }
       if (tid == 0) {
         // state that advanced in registers during quiet blocks
