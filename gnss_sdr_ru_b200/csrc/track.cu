@@ -472,11 +472,10 @@ __device__ __forceinline__ void warp_sum6(int (&v)[6]) {
   }
 }
 
-#define SPT 32
 // dynamic shared memory: two sample tiles of tile_bytes each (TMA mode only)
 // FMT >= 0 fixes the sample format at compile time (the TMA-staged hot variants); FMT < 0 reads it from
 // the arguments (generic variant: unaligned / ragged / I-only blocks, loaded straight from global memory).
-template <int MAXT, int MINB, int FMT, bool TMA>
+template <int MAXT, int MINB, int FMT, bool TMA, int SPT = 32>
 __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs a, const int tile_bytes) {
   constexpr bool use_tma = TMA;
   const int fmt = FMT >= 0 ? FMT : a.fmt;
@@ -848,7 +847,6 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
     if (a.dump_count) a.dump_count[s * NCH + ch] = cs.dump_count;
   }
 }
-#undef SPT
 
 // one thread per stream: status words, TIC counter and block counter after a run
 __global__ void track_finish_kernel(gnssb200_rx *rx, const int32_t *chan_flags, int first_stream, int n_streams,
@@ -928,7 +926,12 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   a.dump_count = d_dump_count;
   a.cfg = h->cfg;
   const int grid = n_streams * NCH;
-  const int spt = 32;
+  static int env_spt = -1;
+  if (env_spt < 0) {
+    const char *e = getenv("GNSSB200_TRACK_SPT");
+    env_spt = e ? atoi(e) : 0;
+  }
+  const int spt = (env_spt == 16 && nsamp == 8192) ? 16 : 32;
   int threads = (nsamp + spt - 1) / spt;
   threads = ((threads + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
@@ -941,7 +944,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     const char *e = getenv("GNSSB200_TRACK_NO_TMA");
     no_tma = (e && atoi(e)) ? 1 : 0;
   }
-  const int use_tma = (aligned && !no_tma && nsamp <= 256 * spt && blk_bytes <= 16384) ? 1 : 0;
+  const int use_tma = (aligned && !no_tma && nsamp <= (spt == 16 ? 512 : 256) * spt && blk_bytes <= 16384) ? 1 : 0;
   const int tile_bytes = use_tma ? (int)((blk_bytes + 127) & ~(size_t)127) : 0;
   const size_t dyn = (size_t)2 * tile_bytes;
   static bool attr_done = false;
@@ -963,6 +966,14 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const bool dense = force_occ ? (force_occ >= 4) : (grid > 3 * sms);
   const bool hot = use_tma && threads <= 256 && (fmt == GNSSB200_FMT_INT8_IQ || fmt == GNSSB200_FMT_PACKED2);
+  if (spt == 16 && use_tma && fmt == GNSSB200_FMT_PACKED2) {  // experiment: 512 threads x 16 samples
+    static bool a16 = false;
+    if (!a16) {
+      CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+      a16 = true;
+    }
+    track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16><<<grid, 512, dyn, st>>>(a, tile_bytes);
+  } else
   if (hot && fmt == GNSSB200_FMT_INT8_IQ && dense)
     track_loop_kernel<256, 4, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
   else if (hot && fmt == GNSSB200_FMT_INT8_IQ)

@@ -153,3 +153,62 @@ def test_acq_vs_committed_fixture():
     assert [int(x) for x in res["codePhaseRaw"]] == [int(x) for x in g["codePhaseRaw"]]
     assert np.allclose(res["peakMetric"], g["peakMetric"], rtol=RTOL)
     assert np.allclose(res["rows"]["peak"], g["rows"][:, :, 0], rtol=RTOL)
+
+
+def test_c1_full_grid_vs_oracle(oracle_lib):
+    """BASELINE config 1 at full size: 32 PRNs x 41 bins x 16000 code phases (21.0 M cells)."""
+    from oracle import pcps_oracle as po
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.scenarios import gps_acq_scenario
+    from gnss_sdr_ru_b200.synth import make_record
+
+    rec = make_record(gps_acq_scenario(1001), 16000 * 3, seed=1001)
+    st = Settings.gps(acqSearchBand=20.0, acqCohIntegration=1)
+    eng = AcquisitionEngine()
+    res = eng.acquisition(rec, st, return_rows=True)
+    assert eng.cells(st) == 32 * 41 * 16000
+    ora = po.acquisition(po.to_complex(rec), po.AcqSettings.gps(acqSearchBand=20.0, acqCohIntegration=1))
+    _check(res, ora, res["rows"], 41)
+
+
+def test_c3_half_grid_vs_oracle(oracle_lib):
+    """BASELINE config 3 settings (5 ms, 12 kHz, 121 bins) on 7 of the 14 frequency channels
+    (the float64 oracle needs ~2 s per channel)."""
+    from oracle import pcps_oracle as po
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.scenarios import glonass_acq_scenario
+    from gnss_sdr_ru_b200.synth import make_record
+
+    rec = make_record(glonass_acq_scenario(3003), 16000 * 11, seed=3003)
+    fch = [-7, -5, -4, -1, 0, 3, 6]
+    st = Settings.glonass(acqSatelliteList=fch)
+    res = AcquisitionEngine().acquisition(rec, st, return_rows=True)
+    ora = po.acquisition(po.to_complex(rec), po.AcqSettings.glonass(svList=fch))
+    _check(res, ora, res["rows"], 121)
+
+
+def test_c4_full_size_finds_the_generated_satellites():
+    """BASELINE config 4 at full size (32 PRN x 401 bins, 10 ms x 20 non-coherent, 205 M cells): a
+    size-independent property instead of the (hours-long) float64 oracle -- every satellite the
+    generator put into the record at >= 33 dB-Hz is detected at its true Doppler bin and code phase."""
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.scenarios import gps_weak_acq_scenario
+    from gnss_sdr_ru_b200.synth import make_record
+
+    sats = gps_weak_acq_scenario(4004)
+    for s in sats:
+        s.cn0_dbhz = max(s.cn0_dbhz, 36.0)
+    rec = make_record(sats, 16000 * 200, seed=4004)
+    st = Settings.gps(acqSearchBand=20.0, acqCohIntegration=10, n_noncoh=20)
+    res = AcquisitionEngine().acquisition(rec, st)
+    for s in sats:
+        i = s.prn - 1
+        assert int(res["freqChannel"][i]) == s.prn, (s.prn, res["peakMetric"][i])
+        assert abs(res["carrFreq"][i] - (2.42e6 + s.doppler_hz)) <= 50.0
+        # code phase: the record starts at chip `code_phase_chips`; the replica aligns at sample
+        # (1023 - phase) * 16000/1023 (mod 16000), 1-based in the result
+        want = ((1023.0 - s.code_phase_chips) % 1023.0) * 16000.0 / 1023.0
+        d = abs(((res["codePhase"][i] - 1) - want + 8000.0) % 16000.0 - 8000.0)
+        assert d <= 16.0, (s.prn, res["codePhase"][i], want)
+    absent = [p for p in range(1, 33) if p not in {s.prn for s in sats}]
+    assert sum(int(res["freqChannel"][p - 1]) != 0 for p in absent) == 0

@@ -1,6 +1,6 @@
 # ad-hoc timing probe (not the bench): tracking throughput vs streams / SPT
 import sys, time, ctypes as C, numpy as np, torch
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from gnss_sdr_ru_b200 import abi
 from gnss_sdr_ru_b200.receiver import TrackingEngine
 from gnss_sdr_ru_b200.scenarios import gps_tracking_scenario, synth_sat_array, apply_tracking_scenario
