@@ -9,6 +9,7 @@ marshals arguments.  No CPU implementation exists here.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -78,9 +79,7 @@ class AcquisitionEngine:
         self.h = None
 
     def __del__(self):
-        import sys
-
-        if sys.is_finalizing():  # CUDA may already be torn down at interpreter exit
+        if sys is None or sys.is_finalizing():  # CUDA may already be torn down at interpreter exit
             return
         try:
             self.close()

@@ -11,6 +11,7 @@ OSG/osgnss_next_step.c:41-84): ``ch_cntl``, ``ch_carrier``, ``ch_code``, ``ch_co
 from __future__ import annotations
 
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -88,9 +89,7 @@ class TrackingEngine:
             self.h = None
 
     def __del__(self):
-        import sys
-
-        if sys.is_finalizing():  # CUDA may already be torn down at interpreter exit
+        if sys is None or sys.is_finalizing():  # CUDA may already be torn down at interpreter exit
             return
         try:
             self.close()
