@@ -375,6 +375,29 @@ def run_ours(args):
                           "hbm_frac": S2 * NS * nb2 * bytes_per_sample / (best * 1e-3) / 1e9 / load_peaks()[0]}
             eng2.close()
             del d2
+        # C1 integer path: GP2021-semantics serial search, detection threshold out of reach,
+        # 500 Hz bins; one dump of one channel = one search cell (PRN x Doppler bin x half-chip delay)
+        from gnss_sdr_ru_b200.lib import default_cfg
+
+        secs = min(args.seconds, 3.0)
+        nb3 = int(secs * FS / NS)
+        eng3 = TrackingEngine(n_streams=S, device=local, cfg=default_cfg(acq_thresh=2**30, freq_bin_width=500.0))
+        for s in range(S):
+            eng3.simple_cold_allocate(s, [1 + (12 * s + c) % 32 for c in range(12)])
+            for c in range(12):
+                eng3.rx[s].chan[c].search_max_f = 20
+        eng3.upload()
+        cnt3 = torch.zeros((S, 12), dtype=torch.int32, device=dev)
+        dmp3 = torch.empty((S, 12, int(secs * 1000) + 64, 48), dtype=torch.uint8, device=dev)
+        eng3.run_device(d_if.data_ptr(), d_if.stride(0), nb3, NS, fmt, d_dumps_ptr=dmp3.data_ptr(), dump_cap=dmp3.shape[2],
+                        d_count_ptr=cnt3.data_ptr(), stream=stream.cuda_stream)
+        stream.synchronize()
+        ms3 = eng3.last_kernel_ms()
+        cells3 = int(cnt3.sum().item())
+        also["C1_integer_serial_search"] = {"streams": S, "channels": 12 * S, "seconds": secs, "kernel_ms": ms3, "cells": cells3,
+                                            "cells_per_s": cells3 / (ms3 * 1e-3),
+                                            "note": "threshold out of reach, 500 Hz bins, search_max_f=20; reference C receiver: ~18e3 cells/s per core"}
+        eng3.close()
 
     # ---- acquisition (configs 1, 3, 4), outside the timed steps ----
     acq = None

@@ -168,3 +168,23 @@ class TrackingEngine:
 
     def last_kernel_ms(self) -> float:
         return float(self.L.gnssb200_last_kernel_ms(self.h))
+
+
+def serial_search_cell_map(dumps: np.ndarray, counts: np.ndarray):
+    """Turn the dump records of a run with the detection threshold out of reach into the GP2021-semantics
+    search cell map {(stream, channel): array of (n_freq, code delay in half chips, IP, QP, rss)}.
+    One dump = one cell ("serial-search schedule"); the record of a dump carries the
+    bin / delay the channel moved to AFTER the dump, so cell k is described by record k-1."""
+    out = {}
+    S, nch, _ = dumps.shape
+    for s in range(S):
+        for ch in range(nch):
+            d = dumps[s, ch, : counts[s, ch]]
+            if len(d) < 2:
+                continue
+            ip = d["acc"][1:, 2].astype(np.int64)
+            qp = d["acc"][1:, 3].astype(np.int64)
+            a, b = np.abs(ip), np.abs(qp)
+            rss = np.where(a > b, a + (b >> 1), b + (a >> 1))  # rss(), osgpsisr.c:77-91
+            out[(s, ch)] = np.stack([d["n_freq"][:-1].astype(np.int64), d["codes"][:-1].astype(np.int64), ip, qp, rss], axis=1)
+    return out

@@ -205,3 +205,33 @@ def test_closed_loop_vs_reference_golden():
     assert np.array_equal(dumps[0], g["dumps"].view(abi.DUMP_DTYPE).reshape(dumps[0].shape))
     assert np.array_equal(np.array(eng.rx[0].reg_read[:]), g["reg_read"])
     assert np.array_equal(np.array(eng.rx[0].reg_write[:]), g["reg_write"])
+
+
+def test_serial_search_bin_stepping(oracle_lib, track_record):
+    """GP2021-semantics serial search (ch_acq, osgpsisr.c:424-459) with the detection threshold out of
+    reach: every dump is one search cell.  A short code-delay range (50 half chips) and +-2 bins make the
+    channels step through Doppler bins 0,+1,-1,+2,-2, overflow search_max_f and restart within the run,
+    including the carrier step in the middle of a cell (quirk Q6)."""
+    from gnss_sdr_ru_b200.lib import default_cfg
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+
+    rec, _ = track_record
+    nblk = 1300
+    over = dict(acq_thresh=2**30, freq_bin_width=500.0)
+    eng = TrackingEngine(n_streams=1, cfg=default_cfg(**over))
+    o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(**over))
+    prns = [27, 9, 32, 1, 2, 3, 4, 5, 6, 7, 8, 31]
+    eng.simple_cold_allocate(0, prns)
+    o.cold_allocate(prns)
+    for ch in range(12):
+        for k in (eng.rx[0].chan[ch], o.rx.chan[ch]):
+            k.search_max_PRN_delay = 50 + ch
+            k.search_max_f = 2
+    assert _rx_bytes(eng.rx[0]) == _rx_bytes(o.rx)
+    eng.upload()
+    dumps, cnt = _compare_run(eng, [o], rec[None, : 2 * NS * nblk], nblk)
+    d0 = dumps[0, 0, : cnt[0, 0]]
+    # all five bins visited; n_freq = 3 is the overflow value that triggers the restart at the next dump
+    assert set(np.unique(d0["n_freq"])) == {-2, -1, 0, 1, 2, 3}
+    assert (np.diff(np.nonzero(d0["n_freq"] == 3)[0]) > 1).all()
+    assert (d0["state"] == 1).all()
