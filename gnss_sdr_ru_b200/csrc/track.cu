@@ -256,6 +256,59 @@ __device__ __forceinline__ void correlate_chunk(const uint32_t (&w)[SPT / 2], ui
   accL = aL;
 }
 
+// Packed-native variant of the hot loop (GNSSB200_FMT_PACKED2, 32 samples = 16 bytes per thread): the
+// 4-bit sample code (I,Q) and the 3-bit LO phase index a table of the finished mixer outputs
+//   vlut[phase*16 + code][lane] = I*A[phase] + Q*B[phase]   (= ival + 65536*qval, exact small integers),
+// replicated per lane so the look-up is bank-conflict free.  No unpack, no multiplies in the mixer.
+template <int SPT>
+__device__ __forceinline__ void correlate_chunk_packed(const uint32_t (&p)[SPT / 8], uint32_t cph, uint32_t kph,
+                                                       const uint32_t cinc, const uint32_t kinc, const uint32_t *tbl,
+                                                       uint32_t h, uint32_t bits, const uint32_t vlut_lane /* smem byte address of vlut[0][lane] */,
+                                                       int &accE, int &accP, int &accL) {
+  int oE = sext8(bits, 0), oP = sext8(bits, 1), oL = sext8(bits, 2);
+  int aE = 0, aP = 0, aL = 0;
+  uint32_t hp = smem_u32(tbl + h);
+  const uint32_t t1 = 0u - kinc, t2 = 0u - 2u * kinc, t3 = 0u - 3u * kinc, k4 = 4u * kinc;
+#pragma unroll
+  for (int g8 = 0; g8 < SPT / 8; g8++) {
+    const uint32_t word = p[g8];
+    int v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      // entry offset = (phase*16 + code) * 128 bytes: phase -> bits 13..11, code -> bits 10..7
+      const uint32_t ph = (cph >> 18) & 0x3800u;
+      const uint32_t cd = (4 * j >= 7 ? (word >> (4 * j - 7)) : (word << (7 - 4 * j))) & 0x780u;
+      uint32_t t;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(vlut_lane + ph + cd));
+      v[j] = (int)t;
+      cph += cinc;
+    }
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const bool m1 = kph < t1, m2 = kph < t2, m3 = kph < t3;
+      int so = v[4 * g], sn = 0;
+      if (m1) so += v[4 * g + 1]; else sn += v[4 * g + 1];
+      if (m2) so += v[4 * g + 2]; else sn += v[4 * g + 2];
+      if (m3) so += v[4 * g + 3]; else sn += v[4 * g + 3];
+      uint32_t carry;
+      asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(kph), "=r"(carry) : "r"(k4));
+      hp += carry << 2;
+      uint32_t t;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(hp));
+      const int nE = sext8(t, 0), nP = sext8(t, 1), nL = sext8(t, 2);
+      aE += oE * so + nE * sn;
+      aP += oP * so + nP * sn;
+      aL += oL * so + nL * sn;
+      oE = nE;
+      oP = nP;
+      oL = nL;
+    }
+  }
+  accE = aE;
+  accP = aP;
+  accL = aL;
+}
+
 __device__ __forceinline__ void unpack_lanes(int packed, int &lo, int &hi) {
   lo = (int)(short)(packed & 0xffff);
   hi = (packed - lo) >> 16;
@@ -490,6 +543,9 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   __shared__ __align__(16) int totals[12];  // six pre-dump and six post-dump sums, accumulated by shared-memory atomics
   __shared__ __align__(8) uint64_t mbar[2];
   extern __shared__ __align__(128) uint8_t tiles[];
+  constexpr bool packed_native = TMA && FMT == GNSSB200_FMT_PACKED2;
+  // [128 entries][32 lanes] mixer-output table of the packed-native loop, placed after the two tiles
+  uint32_t *vlut = reinterpret_cast<uint32_t *>(tiles + 2 * (size_t)tile_bytes);
 
   const int s = a.first_stream + blockIdx.x / NCH, ch = blockIdx.x % NCH;
   gnssb200_rx *rx = a.rx + s;
@@ -501,6 +557,17 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   for (int i = tid; i < SMEM_TBL; i += blockDim.x) {
     long long f = (long long)tbl_prn * HALF_CHIPS + i;
     tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+  }
+  if (packed_native) {
+    const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
+    const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
+    const int val[4] = {1, -1, 3, -3};
+    for (int i = tid; i < 128 * 32; i += blockDim.x) {
+      const int e = i >> 5, ph = e >> 4, code = e & 15;
+      const int I = val[code & 3], Q = val[code >> 2];
+      const int ival = i_lo[ph] * I + q_lo[ph] * Q, qval = q_lo[ph] * I - i_lo[ph] * Q;  // correlator.c:214-215
+      vlut[i] = (uint32_t)(ival + 65536 * qval);
+    }
   }
   if (tid < 48) {
     long long f = (long long)tbl_prn * HALF_CHIPS + tid;
@@ -628,17 +695,22 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
         const int i0 = base + my_i0;
         const bool live = i0 < a.nsamp;
         uint32_t cur[SPT / 2];
+        uint32_t pk[SPT / 8];
 #ifdef TRACK_PROFILE
         long long l0c = clock64();
 #endif
-        if (live) {
+        if (live && packed_native) {
+          const uint32_t *pp = reinterpret_cast<const uint32_t *>(tile + (i0 >> 1));
+#pragma unroll
+          for (int q = 0; q < SPT / 8; q++) pk[q] = pp[q];
+        } else if (live) {
           if (use_tma)
             load_chunk<SPT, true>(tile, fmt, i0, a.nsamp, true, unpack_lut, cur);  // shared-memory tile
           else
             load_chunk<SPT>(blk, fmt, i0, a.nsamp, aligned, unpack_lut, cur);
         }
 #ifdef TRACK_PROFILE
-        t_load += clock64() - l0c + (cur[0] & 0);
+        t_load += clock64() - l0c;
 #endif
         const int i1 = live ? min(i0 + SPT, a.nsamp) : i0 + 1;
         const unsigned long long k0 = (unsigned long long)sp.kph0 + (unsigned long long)i0 * sp.kinc;
@@ -659,7 +731,11 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
 #endif
         // chunk starting in the first post-dump half chip: stale bits first, then tbl[1], tbl[2], ...
         const bool stale_start = allB && h == 0;
-        if (live)
+        if (live && packed_native)
+          correlate_chunk_packed<SPT>(pk, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc,
+                                      stale_start ? alias_tbl : tbl, h, stale_start ? sp.stale_bits : tbl[hl],
+                                      smem_u32(vlut) + 4u * (uint32_t)lane, pE, pP, pL);
+        else if (live)
           correlate_chunk<SPT>(cur, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc,
                                stale_start ? alias_tbl : tbl, h, stale_start ? sp.stale_bits : tbl[hl], lut, pE, pP, pL);
 #ifdef TRACK_PROFILE
@@ -946,13 +1022,13 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   }
   const int use_tma = (aligned && !no_tma && nsamp <= (spt == 16 ? 512 : 256) * spt && blk_bytes <= 16384) ? 1 : 0;
   const int tile_bytes = use_tma ? (int)((blk_bytes + 127) & ~(size_t)127) : 0;
-  const size_t dyn = (size_t)2 * tile_bytes;
+  const size_t dyn = (size_t)2 * tile_bytes + ((use_tma && fmt == GNSSB200_FMT_PACKED2) ? 128 * 32 * 4 : 0);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
     CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
+    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
     attr_done = true;
   }
   // few channels per SM: 128 registers buy instruction-level parallelism for the shared-memory look-ups;
@@ -969,7 +1045,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   if (spt == 16 && use_tma && fmt == GNSSB200_FMT_PACKED2) {  // experiment: 512 threads x 16 samples
     static bool a16 = false;
     if (!a16) {
-      CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+      CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
       a16 = true;
     }
     track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16><<<grid, 512, dyn, st>>>(a, tile_bytes);
