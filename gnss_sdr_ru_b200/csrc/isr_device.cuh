@@ -55,16 +55,6 @@ __device__ __forceinline__ long long dev_mag(long long a, long long b) {  // rss
   return (c > d) ? (d >> 1) + c : (c >> 1) + d;
 }
 
-// trunc(a / b) for 64-bit integers.  For abs(a) < 2^52 the correctly rounded FP64 quotient cannot cross
-// an integer (a non-integer quotient is at least 1/abs(b) >= 2^-31 away from one, far more than the
-// 2^-53 relative rounding error), so FP64 division + truncation is exact; it is several times
-// shorter than the 64-bit integer division sequence on this GPU.
-__device__ __forceinline__ long long dev_div64(long long a, long long b) {
-  const long long aa = a < 0 ? -a : a;
-  if (aa < (1ll << 52) && b > -(1ll << 31) && b < (1ll << 31)) return (long long)((double)a / (double)b);
-  return a / b;
-}
-
 // sqrt_newton() (osgpsisr.c:148-178).  For every argument 0 < L < 2^31 -- the reference only passes
 // sums of two squared shorts -- the Newton iteration of the reference returns
 //        max { x : x*(x-1) <= L }
@@ -101,34 +91,52 @@ __device__ __forceinline__ unsigned dev_isqrt(long long L) {
 }
 
 // fix_atan2() (osgpsisr.c:199-231), 1 rad = 16384.  The divisor is always the operand of larger
-// magnitude, so abs(n) <= 2^14 and the cubic correction fits 32-bit arithmetic; the one real division is
-// done in FP64 (exact, see dev_div64).
+// magnitude, so abs(n) <= 2^14 and the cubic correction fits 32-bit arithmetic.
 __device__ __forceinline__ int dev_atan2_n3(int n) {  // ((((n*n)>>14)*n)>>13)/9 with abs(n) <= 2^14
   return ((((n * n) >> 14) * n) >> 13) / 9;
 }
-__device__ __noinline__ long long dev_atan2(long long y, long long x) {
-  const long long half_pi = 25736, pi = 51472;
-  long long res = 0;
-  if (x == 0 && y == 0) return 0;
-  const bool small = y > -(1ll << 31) && y < (1ll << 31) && x > -(1ll << 31) && x < (1ll << 31);
-  if (x > 0 && x >= dev_abs_trunc(y)) {
-    const long long n = dev_div64(y << 14, x);
-    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
-    res = n - n3;
-  } else if (x <= 0 && -x >= dev_abs_trunc(y)) {
-    const long long n = dev_div64(y << 14, x);
-    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
-    res = (y > 0) ? n - n3 + pi : n - n3 - pi;
-  } else if (y > 0 && y > dev_abs_trunc(x)) {
-    const long long n = dev_div64(x << 14, y);
-    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
-    res = half_pi - n + n3;
-  } else if (y < 0 && -y > dev_abs_trunc(x)) {
-    const long long n = dev_div64(x << 14, y);
-    const long long n3 = small ? (long long)dev_atan2_n3((int)n) : ((((n * n) >> 14) * n) >> 13) / 9;
-    res = -n + n3 - half_pi;
+// trunc((y << 14) / x) for abs(y) <= abs(x) < 2^31, x != 0 (so abs(quotient) <= 2^14): float estimate
+// (error < 1) corrected with exact 64-bit remainders.
+__device__ __forceinline__ int dev_div_q14(int y, int x) {
+  const unsigned long long A = (unsigned long long)(unsigned)(y < 0 ? -y : y) << 14;
+  const unsigned B = (unsigned)(x < 0 ? -x : x);
+  unsigned q = (unsigned)__fdividef((float)A, (float)B);
+  long long rem = (long long)A - (long long)((unsigned long long)q * B);
+  while (rem < 0) {
+    q--;
+    rem += B;
   }
-  return res;
+  while (rem >= (long long)B) {
+    q++;
+    rem -= B;
+  }
+  return ((y < 0) != (x < 0)) ? -(int)q : (int)q;
+}
+
+// fix_atan2() for arguments that fit int32 (always the case for the dumps of the reference: they are
+// shorts and products of shorts shifted right by 8): same branches, same truncations, 32-bit arithmetic.
+__device__ __forceinline__ int dev_atan2_i32(int y, int x) {
+  const int half_pi = 25736, pi = 51472;
+  if (x == 0 && y == 0) return 0;
+  const int ay = y < 0 ? -y : y, ax = x < 0 ? -x : x;
+  if (x > 0 && x >= ay) {
+    const int n = dev_div_q14(y, x);
+    return n - dev_atan2_n3(n);
+  }
+  if (x <= 0 && -x >= ay) {
+    const int n = dev_div_q14(y, x);
+    const int r = n - dev_atan2_n3(n);
+    return y > 0 ? r + pi : r - pi;
+  }
+  if (y > 0 && y > ax) {
+    const int n = dev_div_q14(x, y);
+    return half_pi - n + dev_atan2_n3(n);
+  }
+  if (y < 0 && -y > ax) {
+    const int n = dev_div_q14(x, y);
+    return -n + dev_atan2_n3(n) - half_pi;
+  }
+  return 0;
 }
 
 // indices into gnssb200_chan.accum[]
@@ -201,14 +209,18 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
     k.dot = dt < 0 ? -dt : dt;
     k.cross >>= 8;
     k.dot >>= 8;
-    k.freqError = dev_atan2(k.cross, k.dot);
-    long long aip = ip < 0 ? -(long long)ip : (long long)ip;
-    k.carrError = dev_atan2((long long)(qp * dev_sgn(ip)), aip) / 2;
+    // operands: abs(cross), dot < 2^23 and abs(qp), abs(ip) <= 2^15 (shorts) -> the int32 form is exact
+    k.freqError = (long long)dev_atan2_i32((int)k.cross, (int)k.dot);
+    k.carrError = (long long)(dev_atan2_i32(qp * dev_sgn(ip), ip < 0 ? -ip : ip) / 2);
   } else {
     k.freqError = 0;
     k.carrError = k.oldCarrError;
   }
-  k.carrNco = k.oldCarrNco + (c.pll_i1 * k.carrError - c.pll_i2 * k.oldCarrError - c.pll_i3 * k.freqError) / 51472;
+  {
+    const long long num = c.pll_i1 * k.carrError - c.pll_i2 * k.oldCarrError - c.pll_i3 * k.freqError;
+    const long long q = (num == (long long)(int)num) ? (long long)((int)num / 51472) : num / 51472;
+    k.carrNco = k.oldCarrNco + q;
+  }
   k.oldCarrNco = k.carrNco;
   k.oldCarrError = k.carrError;
   k.carrFreq = k.carrFreqBasis + k.carrNco;
@@ -221,7 +233,11 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
     k.codeError = (long long)(num / ((int)se + (int)sl));
   } else
     k.codeError = k.oldCodeError;
-  k.codeNco = k.oldCodeNco + (((c.dll_i1 + 1) * k.codeError - c.dll_i2 * k.oldCodeError) / 8192);
+  {
+    const long long num = (c.dll_i1 + 1) * k.codeError - c.dll_i2 * k.oldCodeError;
+    const long long q = (num == (long long)(int)num) ? (long long)((int)num / 8192) : num / 8192;
+    k.codeNco = k.oldCodeNco + q;
+  }
   k.oldCodeNco = k.codeNco;
   k.oldCodeError = k.codeError;
   k.codeFreq = k.codeFreqBasis - k.codeNco;
