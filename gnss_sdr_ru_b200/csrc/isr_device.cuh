@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 
+
 // The slice of REG_write / REG_read that belongs to one channel.
 struct ChRegs {
   int w_prn;        // REG_write[ch*8+0]
@@ -65,10 +66,11 @@ __device__ __forceinline__ unsigned dev_isqrt(long long L) {
   if (L <= 0) return 0;
   if (L < (1ll << 31)) {
     const unsigned l = (unsigned)L;
-    unsigned x = (unsigned)(sqrtf((float)l) + 0.5f);
+    unsigned x = (unsigned)(sqrtf((float)l) + 0.5f);  // within +-1 of the answer
     if (x == 0) x = 1;
-    while ((unsigned long long)x * (x - 1) > l) x--;
-    while ((unsigned long long)(x + 1) * x <= l) x++;
+    // x <= 46342 here, so x*(x+1) < 2^32: exact 32-bit tests
+    while (x * (x - 1) > l) x--;
+    while ((x + 1) * x <= l) x++;
     return x;
   }
   long long t, div;
@@ -98,19 +100,48 @@ __device__ __forceinline__ int dev_atan2_n3(int n) {  // ((((n*n)>>14)*n)>>13)/9
 // trunc((y << 14) / x) for abs(y) <= abs(x) < 2^31, x != 0 (so abs(quotient) <= 2^14): float estimate
 // (error < 1) corrected with exact 64-bit remainders.
 __device__ __forceinline__ int dev_div_q14(int y, int x) {
-  const unsigned long long A = (unsigned long long)(unsigned)(y < 0 ? -y : y) << 14;
-  const unsigned B = (unsigned)(x < 0 ? -x : x);
-  unsigned q = (unsigned)__fdividef((float)A, (float)B);
-  long long rem = (long long)A - (long long)((unsigned long long)q * B);
-  while (rem < 0) {
-    q--;
-    rem += B;
-  }
-  while (rem >= (long long)B) {
-    q++;
-    rem -= B;
+  const unsigned ay = (unsigned)(y < 0 ? -y : y), B = (unsigned)(x < 0 ? -x : x);
+  unsigned q = (unsigned)__fdividef((float)ay * 16384.0f, (float)B);
+  if (B < (1u << 30)) {
+    // true remainder lies in (-B, 2B), inside int32: wrapping 32-bit arithmetic recovers it exactly
+    int rem = (int)((ay << 14) - q * B);
+    while (rem < 0) {
+      q--;
+      rem += (int)B;
+    }
+    while (rem >= (int)B) {
+      q++;
+      rem -= (int)B;
+    }
+  } else {
+    const unsigned long long A = (unsigned long long)ay << 14;
+    long long rem = (long long)A - (long long)((unsigned long long)q * B);
+    while (rem < 0) {
+      q--;
+      rem += B;
+    }
+    while (rem >= (long long)B) {
+      q++;
+      rem -= B;
+    }
   }
   return ((y < 0) != (x < 0)) ? -(int)q : (int)q;
+}
+
+// trunc(num / den) for abs(num) < 2^30, 0 < den < 2^20 and abs(quotient) < 2^20 (C semantics: toward zero)
+__device__ __forceinline__ int dev_div_small(int num, int den) {
+  const unsigned an = (unsigned)(num < 0 ? -num : num);
+  unsigned q = (unsigned)__fdividef((float)an, (float)den);
+  int rem = (int)(an - q * (unsigned)den);
+  while (rem < 0) {
+    q--;
+    rem += den;
+  }
+  while (rem >= den) {
+    q++;
+    rem -= den;
+  }
+  return num < 0 ? -(int)q : (int)q;
 }
 
 // fix_atan2() for arguments that fit int32 (always the case for the dumps of the reference: they are
@@ -230,7 +261,7 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
     unsigned se = dev_isqrt((long long)(ie * ie + qe * qe)), sl = dev_isqrt((long long)(il * il + ql * ql));
     // (8192*(se-sl))/(se+sl): se, sl <= 46341, so everything fits int32 (C division truncates toward zero)
     const int num = 8192 * ((int)se - (int)sl);
-    k.codeError = (long long)(num / ((int)se + (int)sl));
+    k.codeError = (long long)dev_div_small(num, (int)se + (int)sl);  // abs(num) <= 2^29.5, den <= 92684, abs(q) <= 8192
   } else
     k.codeError = k.oldCodeError;
   {
