@@ -398,6 +398,31 @@ def run_ours(args):
                                             "cells_per_s": cells3 / (ms3 * 1e-3),
                                             "note": "threshold out of reach, 500 Hz bins, search_max_f=20; reference C receiver: ~18e3 cells/s per core"}
         eng3.close()
+        # floating-point (Scilab) tracking, 8 GLONASS channels x 2 s, FP64
+        from gnss_sdr_ru_b200.softtrack import SoftTrackingEngine, TrackSettings
+        from gnss_sdr_ru_b200.scenarios import TrackScenario
+        from gnss_sdr_ru_b200.synth import Sat
+
+        fsats = [Sat(system="glonass", prn=k, cn0_dbhz=48.0, doppler_hz=400.0 * k, code_phase_chips=37.0 * (k + 8),
+                     data_seed=50 + k, data_rate_hz=100.0) for k in (-7, -5, -3, -1, 0, 2, 4, 6)]
+        fms = 2000
+        fn = 16000 * (fms + 8)
+        frec = torch.empty(2 * fn, dtype=torch.uint8, device=dev)
+        farr, fns = synth_sat_array([TrackScenario(sats=fsats, prns=[], n_freq=[])])
+        check(L.gnssb200_synth(eng.h, frec.data_ptr(), 2 * fn, abi.FMT_INT8_IQ, 1, fn, C.addressof(farr), fns, 77, None), "gnssb200_synth")
+        fchan = [dict(FCH=s_.prn, acquiredFreq=1e6 + 562500.0 * s_.prn + s_.doppler_hz + 30.0,
+                      codePhase=int(round((511.0 - s_.code_phase_chips % 511.0) * 16000.0 / 511.0)) % 16000 + 1) for s_ in fsats]
+        fout = torch.zeros((len(fchan), fms, 13), dtype=torch.float64, device=dev)
+        fdone = torch.zeros(len(fchan), dtype=torch.int32, device=dev)
+        ste = SoftTrackingEngine(handle=eng.h)
+        for it in range(2):
+            ste.tracking_device(frec.data_ptr(), fn, fchan, TrackSettings(msToProcess=fms), fout.data_ptr(), fdone.data_ptr())
+        fms_t = ste.last_kernel_ms()
+        ip = fout[:, -200:, 1].abs().mean(dim=1).cpu().numpy()
+        qp = fout[:, -200:, 4].abs().mean(dim=1).cpu().numpy()
+        also["scilab_float_tracking_glonass"] = {"channels": len(fchan), "ms": fms, "kernel_ms": fms_t,
+                                                 "channel_Msamples_per_s": len(fchan) * 16000.0 * fms / (fms_t * 1e-3) / 1e6,
+                                                 "channels_locked": int((ip > 3 * qp).sum()), "dtype": "f64"}
 
     # ---- acquisition (configs 1, 3, 4), outside the timed steps ----
     acq = None

@@ -185,6 +185,33 @@ class AcqResult(C.Structure):
     ]
 
 
+class SoftTrackCfg(C.Structure):
+    _fields_ = [
+        ("system", C.c_int32),
+        ("code_length", C.c_int32),
+        ("samp_freq", C.c_double),
+        ("IF", C.c_double),
+        ("IF_step", C.c_double),
+        ("glonass_zero_channel", C.c_double),
+        ("code_freq", C.c_double),
+        ("dll_damping_ratio", C.c_double),
+        ("dll_noise_bandwidth", C.c_double),
+        ("dll_correlator_spacing", C.c_double),
+        ("pll_noise_bandwidth", C.c_double),
+        ("fll_noise_bandwidth", C.c_double),
+        ("skip_samples", C.c_int64),
+        ("ms_to_process", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class SoftTrackChan(C.Structure):
+    _fields_ = [("sv", C.c_int32), ("code_phase", C.c_int32), ("acquired_freq", C.c_double)]
+
+
+SOFTTRACK_FIELDS = ("I_E", "I_P", "I_L", "Q_E", "Q_P", "Q_L", "carrFreq", "codeFreq", "dllDiscr", "dllDiscrFilt",
+                    "pllDiscr", "pllDiscrFilt", "absoluteSample")
+
 assert C.sizeof(Dump) == 48
 DUMP_DTYPE = [
     ("block", "<i4"),

@@ -276,6 +276,42 @@ int gnssb200_acq_finalize(const gnssb200_acq_cfg *cfg, const gnssb200_acq_row *h
 int gnssb200_acq_pcps_host(gnssb200_handle *h, const gnssb200_acq_cfg *cfg, const void *h_iq, int fmt,
                            int64_t n_samples, gnssb200_acq_result *results, gnssb200_acq_row *h_rows_opt);
 
+/* ---------------------------------------------------------------------------------------------
+ * (2) batched layer -- floating-point tracking of the Scilab receivers
+ *     [trackResults, channel] = tracking(fid, channel, settings)
+ *     SCI/GLONASS/L1/tracking.sci:226-400, SCI/GPS/L1/tracking.sci; channel list as built by
+ *     SCI/x/include/preRun.sci:66-81 from acqResults.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gnssb200_softtrack_cfg {
+  int32_t system;                 /* GNSSB200_SYS_* */
+  int32_t code_length;            /* settings.codeLength */
+  double samp_freq;               /* settings.samplingFreq */
+  double IF;                      /* settings.IF */
+  double IF_step;                 /* settings.L1_IF_step (GLONASS) */
+  double glonass_zero_channel;    /* settings.GLONASS_zero_channel 1602e6 */
+  double code_freq;               /* settings.codeFreqBasis */
+  double dll_damping_ratio, dll_noise_bandwidth, dll_correlator_spacing;
+  double pll_noise_bandwidth, fll_noise_bandwidth;
+  int64_t skip_samples;           /* settings.skipNumberOfBytes in complex samples */
+  int32_t ms_to_process;          /* settings.msToProcess */
+  int32_t pad_;
+} gnssb200_softtrack_cfg;
+
+typedef struct gnssb200_softtrack_chan {   /* one entry of the `channel` struct array */
+  int32_t sv;                     /* PRN (GPS) / FCH (GLONASS) */
+  int32_t code_phase;             /* channel.codePhase, 1-based sample */
+  double acquired_freq;           /* channel.acquiredFreq */
+} gnssb200_softtrack_chan;
+
+#define GNSSB200_SOFTTRACK_FIELDS 13 /* I_E I_P I_L Q_E Q_P Q_L carrFreq codeFreq dllDiscr dllDiscrFilt pllDiscr pllDiscrFilt absoluteSample */
+
+/* d_iq: device int8 I,Q record (the whole file); d_out: device double [n_ch][ms_to_process][13];
+ * d_ms_done: device int32 [n_ch] = code periods actually processed (fewer if the record ends).
+ * Synchronous on cuda_stream. */
+int gnssb200_softtrack(gnssb200_handle *h, const gnssb200_softtrack_cfg *cfg, const void *d_iq, int64_t n_samples,
+                       const gnssb200_softtrack_chan *chans, int n_ch, double *d_out, int32_t *d_ms_done,
+                       void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
