@@ -4,7 +4,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../libgnssb200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS="--expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-Wall -Xptxas -v -cudart static"
+FLAGS="--expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-Wall -Xptxas -v -cudart static ${EXTRA_NVCC_FLAGS:-}"
 mkdir -p "$HERE/build"
 for f in track api acq synth softtrack; do
   if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ -n "$(find "$HERE" "$HERE/../../include" -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer "$HERE/build/$f.o" 2>/dev/null)" ]; then

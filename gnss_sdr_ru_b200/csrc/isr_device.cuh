@@ -25,10 +25,25 @@ struct ChRegs {
 
 __device__ __forceinline__ int reg16(int v) { return (int)(uint16_t)v; }  // outpwd(): unsigned short
 
-__device__ __forceinline__ void dev_put_nco(int &hi, int &lo, long long freq, int bits, double mult) {
-  long long w = freq << (32 - bits);
-  // gp2021.c:90-91 / 109-110: long * (double)5 -> long.  For an integral multiplier and abs(w) < 2^40 the
-  // product is exact in double, so the integer product is the same value.
+// Receiver constants plus what the device ISR derives from them once per launch (host side, track_launch).
+struct DevCfg : gnssb200_cfg {
+  int mult_i;  // clock_mult when it is an integer in (-1024, 1024), else 0
+};
+
+__device__ __forceinline__ void dev_put_nco(int &hi, int &lo, long long freq, int bits, const DevCfg &c) {
+  // gp2021.c:90-91 / 109-110: long w = freq << (32-N); w = w * (double)5 -> long; the two 16-bit halves of
+  // the low word go to the registers.  For an integral multiplier and abs(w) < 2^40 the product is exact in
+  // double, so the integer product is the same value -- and only its low 32 bits are kept, so for
+  // frequencies inside int32 the whole thing is one 32-bit shift and multiply.
+  const int sh = 32 - bits;
+  if (c.mult_i != 0 && sh >= 0 && sh <= 8 && freq == (long long)(int)freq) {
+    const unsigned w = ((unsigned)(int)freq << sh) * (unsigned)c.mult_i;
+    hi = (int)(w >> 16);
+    lo = (int)(w & 0xffffu);
+    return;
+  }
+  long long w = freq << sh;
+  const double mult = c.clock_mult;
   const long long im = (long long)mult;
   if ((double)im == mult && w > -(1ll << 40) && w < (1ll << 40) && im > -1024 && im < 1024)
     w = w * im;
@@ -37,11 +52,11 @@ __device__ __forceinline__ void dev_put_nco(int &hi, int &lo, long long freq, in
   hi = reg16((int)(w >> 16));
   lo = reg16((int)(w & 0xffff));
 }
-__device__ __forceinline__ void dev_ch_carrier(ChRegs &r, const gnssb200_cfg &c, long long f) {
-  dev_put_nco(r.w_carr_hi, r.w_carr_lo, f, c.carrier_nco_bits, c.clock_mult);
+__device__ __forceinline__ void dev_ch_carrier(ChRegs &r, const DevCfg &c, long long f) {
+  dev_put_nco(r.w_carr_hi, r.w_carr_lo, f, c.carrier_nco_bits, c);
 }
-__device__ __forceinline__ void dev_ch_code(ChRegs &r, const gnssb200_cfg &c, long long f) {
-  dev_put_nco(r.w_code_hi, r.w_code_lo, f, c.code_nco_bits, c.clock_mult);
+__device__ __forceinline__ void dev_ch_code(ChRegs &r, const DevCfg &c, long long f) {
+  dev_put_nco(r.w_code_hi, r.w_code_lo, f, c.code_nco_bits, c);
 }
 
 __device__ __forceinline__ long long dev_abs_trunc(long long v) {  // int abs() applied to a long
@@ -60,19 +75,10 @@ __device__ __forceinline__ long long dev_mag(long long a, long long b) {  // rss
 // sums of two squared shorts -- the Newton iteration of the reference returns
 //        max { x : x*(x-1) <= L }
 // (verified exhaustively over all 2^31 - 1 arguments against the reference's own loop, see
-// tests/test_isr_math.py for the sampled regression).  So the value is taken from a float square root
-// and corrected with exact integer tests; larger arguments run the literal iteration.
-__device__ __forceinline__ unsigned dev_isqrt(long long L) {
-  if (L <= 0) return 0;
-  if (L < (1ll << 31)) {
-    const unsigned l = (unsigned)L;
-    unsigned x = (unsigned)(sqrtf((float)l) + 0.5f);  // within +-1 of the answer
-    if (x == 0) x = 1;
-    // x <= 46342 here, so x*(x+1) < 2^32: exact 32-bit tests
-    while (x * (x - 1) > l) x--;
-    while ((x + 1) * x <= l) x++;
-    return x;
-  }
+// tests/test_isr_math.py for the sampled regression).  So the value is taken from an approximate
+// float square root and corrected with exact integer tests, without branches (the lone ISR lane pays
+// the full latency of every taken branch); larger arguments run the literal iteration.
+__device__ __noinline__ unsigned dev_isqrt_newton(long long L) {
   long long t, div;
   unsigned r = (unsigned)L;
   if (L & 0xFFFF0000LL)
@@ -91,40 +97,52 @@ __device__ __forceinline__ unsigned dev_isqrt(long long L) {
     }
   }
 }
+__device__ __forceinline__ unsigned dev_isqrt(long long L) {
+  if (L <= 0) return 0;
+  if (L < (1ll << 31)) {
+    const unsigned l = (unsigned)L;
+    float sf;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"((float)l));
+    unsigned x = (unsigned)(sf + 0.5f);  // within +-1 of the answer; x <= 46342, so x*(x+1) < 2^32
+    x = x == 0 ? 1u : x;
+    x -= (x * (x - 1) > l) ? 1u : 0u;
+    x += ((x + 1) * x <= l) ? 1u : 0u;
+    if (x * (x - 1) > l || (x + 1) * x <= l) {  // never taken if the estimate is within +-1; keeps the result exact regardless
+      while (x * (x - 1) > l) x--;
+      while ((x + 1) * x <= l) x++;
+    }
+    return x;
+  }
+  return dev_isqrt_newton(L);
+}
 
 // fix_atan2() (osgpsisr.c:199-231), 1 rad = 16384.  The divisor is always the operand of larger
 // magnitude, so abs(n) <= 2^14 and the cubic correction fits 32-bit arithmetic.
 __device__ __forceinline__ int dev_atan2_n3(int n) {  // ((((n*n)>>14)*n)>>13)/9 with abs(n) <= 2^14
   return ((((n * n) >> 14) * n) >> 13) / 9;
 }
-// trunc((y << 14) / x) for abs(y) <= abs(x) < 2^31, x != 0 (so abs(quotient) <= 2^14): float estimate
-// (error < 1) corrected with exact 64-bit remainders.
-__device__ __forceinline__ int dev_div_q14(int y, int x) {
-  const unsigned ay = (unsigned)(y < 0 ? -y : y), B = (unsigned)(x < 0 ? -x : x);
-  unsigned q = (unsigned)__fdividef((float)ay * 16384.0f, (float)B);
+// trunc((a << 14) / B) for 0 <= a <= B, 0 < B < 2^31 (so the quotient is <= 2^14): float estimate
+// (error < 1) corrected once in each direction with the exact remainder; a verified slow path keeps
+// the result exact whatever the estimate was.
+__device__ __forceinline__ unsigned dev_udiv_q14(unsigned a, unsigned B) {
+  unsigned q = (unsigned)__fdividef((float)a * 16384.0f, (float)B);
   if (B < (1u << 30)) {
     // true remainder lies in (-B, 2B), inside int32: wrapping 32-bit arithmetic recovers it exactly
-    int rem = (int)((ay << 14) - q * B);
-    while (rem < 0) {
-      q--;
-      rem += (int)B;
-    }
-    while (rem >= (int)B) {
-      q++;
-      rem -= (int)B;
-    }
-  } else {
-    const unsigned long long A = (unsigned long long)ay << 14;
-    long long rem = (long long)A - (long long)((unsigned long long)q * B);
-    while (rem < 0) {
-      q--;
-      rem += B;
-    }
-    while (rem >= (long long)B) {
-      q++;
-      rem -= B;
-    }
+    int rem = (int)((a << 14) - q * B);
+    const bool lo = rem < 0;
+    q -= lo ? 1u : 0u;
+    rem += lo ? (int)B : 0;
+    const bool hi = rem >= (int)B;
+    q += hi ? 1u : 0u;
+    rem -= hi ? (int)B : 0;
+    if (rem < 0 || rem >= (int)B) q = (unsigned)(((unsigned long long)a << 14) / B);
+    return q;
   }
+  return (unsigned)(((unsigned long long)a << 14) / B);
+}
+__device__ __forceinline__ int dev_div_q14(int y, int x) {  // trunc((y << 14) / x), abs(y) <= abs(x), x != 0
+  const unsigned ay = (unsigned)(y < 0 ? -y : y), B = (unsigned)(x < 0 ? -x : x);
+  const unsigned q = dev_udiv_q14(ay, B);
   return ((y < 0) != (x < 0)) ? -(int)q : (int)q;
 }
 
@@ -133,41 +151,35 @@ __device__ __forceinline__ int dev_div_small(int num, int den) {
   const unsigned an = (unsigned)(num < 0 ? -num : num);
   unsigned q = (unsigned)__fdividef((float)an, (float)den);
   int rem = (int)(an - q * (unsigned)den);
-  while (rem < 0) {
-    q--;
-    rem += den;
-  }
-  while (rem >= den) {
-    q++;
-    rem -= den;
-  }
+  const bool lo = rem < 0;
+  q -= lo ? 1u : 0u;
+  rem += lo ? den : 0;
+  const bool hi = rem >= den;
+  q += hi ? 1u : 0u;
+  rem -= hi ? den : 0;
+  if (rem < 0 || rem >= den) q = an / (unsigned)den;
   return num < 0 ? -(int)q : (int)q;
 }
 
 // fix_atan2() for arguments that fit int32 (always the case for the dumps of the reference: they are
-// shorts and products of shorts shifted right by 8): same branches, same truncations, 32-bit arithmetic.
+// shorts and products of shorts shifted right by 8): same case split, same truncations, 32-bit
+// arithmetic, one division, selects instead of the four-way branch.
+//   x > 0, x >= abs(y):   n = (y<<14)/x,  n - n3
+//   x <= 0, -x >= abs(y): n = (y<<14)/x,  n - n3 (+pi if y > 0, else -pi)
+//   y > 0, y > abs(x):    n = (x<<14)/y,  pi/2 - n + n3
+//   y < 0, -y > abs(x):   n = (x<<14)/y,  -n + n3 - pi/2
 __device__ __forceinline__ int dev_atan2_i32(int y, int x) {
   const int half_pi = 25736, pi = 51472;
-  if (x == 0 && y == 0) return 0;
-  const int ay = y < 0 ? -y : y, ax = x < 0 ? -x : x;
-  if (x > 0 && x >= ay) {
-    const int n = dev_div_q14(y, x);
-    return n - dev_atan2_n3(n);
-  }
-  if (x <= 0 && -x >= ay) {
-    const int n = dev_div_q14(y, x);
-    const int r = n - dev_atan2_n3(n);
-    return y > 0 ? r + pi : r - pi;
-  }
-  if (y > 0 && y > ax) {
-    const int n = dev_div_q14(x, y);
-    return half_pi - n + dev_atan2_n3(n);
-  }
-  if (y < 0 && -y > ax) {
-    const int n = dev_div_q14(x, y);
-    return -n + dev_atan2_n3(n) - half_pi;
-  }
-  return 0;
+  const unsigned ay = (unsigned)(y < 0 ? -y : y), ax = (unsigned)(x < 0 ? -x : x);
+  const bool horiz = ax >= ay;  // cases 1, 2 (and x == y == 0)
+  const unsigned num = horiz ? ay : ax, den = horiz ? ax : ay;
+  const unsigned q = dev_udiv_q14(num, den == 0 ? 1u : den);
+  const int n = ((y < 0) != (x < 0)) ? -(int)q : (int)q;
+  const int t = n - dev_atan2_n3(n);
+  const int rh = x > 0 ? t : (y > 0 ? t + pi : t - pi);
+  const int rv = y > 0 ? half_pi - t : -t - half_pi;
+  const int res = horiz ? rh : rv;
+  return (ax | ay) == 0 ? 0 : res;
 }
 
 // indices into gnssb200_chan.accum[]
@@ -178,7 +190,7 @@ __device__ __forceinline__ int dev_atan2_i32(int y, int x) {
 #define A_IE 4
 #define A_QE 5
 
-__device__ __forceinline__ void dev_isr_search(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+__device__ __forceinline__ void dev_isr_search(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   if (abs(k.n_freq) <= k.search_max_f) {
     long long pm = dev_mag(k.accum[A_IP], k.accum[A_QP]);
     if (pm > c.acq_thresh) {
@@ -207,7 +219,7 @@ __device__ __forceinline__ void dev_isr_search(gnssb200_chan &k, ChRegs &r, cons
   k.CN0 = 0;
 }
 
-__device__ __forceinline__ void dev_isr_confirm(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+__device__ __forceinline__ void dev_isr_confirm(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   long long pm = dev_mag(k.accum[A_IP], k.accum[A_QP]);
   long long lm = dev_mag(k.accum[A_IL], k.accum[A_QL]);
   long long em = dev_mag(k.accum[A_IE], k.accum[A_QE]);
@@ -231,18 +243,28 @@ __device__ __forceinline__ void dev_isr_confirm(gnssb200_chan &k, ChRegs &r, con
   k.i_confirm++;
 }
 
-__device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+__device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   const int ip = k.accum[A_IP], qp = k.accum[A_QP], pip = k.prev_accum[A_IP], pqp = k.prev_accum[A_QP];
   const int ie = k.accum[A_IE], qe = k.accum[A_QE], il = k.accum[A_IL], ql = k.accum[A_QL];
+  // The four discriminator primitives are evaluated up front and unconditionally (they are branch-free
+  // and total), so their dependency chains interleave on the single ISR lane; the reference's
+  // conditions select the results below.
+  const int cross8 = (ip * pqp - pip * qp) >> 8;  // int products, as in the reference
+  const int dt = ip * pip + qp * pqp;
+  const int dot8 = (int)((dt < 0 ? 0u - (unsigned)dt : (unsigned)dt) >> 8);  // abs() of the widened value, as the reference
+  // operands: abs(cross), dot < 2^23 and abs(qp), abs(ip) <= 2^15 (shorts) -> the int32 form is exact
+  const int at_f = dev_atan2_i32(cross8, dot8);
+  const int at_p = dev_atan2_i32(qp * dev_sgn(ip), ip < 0 ? -ip : ip);
+  const unsigned se = dev_isqrt((long long)(ie * ie + qe * qe)), sl = dev_isqrt((long long)(il * il + ql * ql));
+  // (8192*(se-sl))/(se+sl): se, sl <= 46341, so everything fits int32 (C division truncates toward zero)
+  const int den_c = (int)se + (int)sl;
+  const int code_q = dev_div_small(8192 * ((int)se - (int)sl), den_c > 0 ? den_c : 1);  // abs(num) <= 2^29.5, den <= 92684, abs(q) <= 8192
+
   if (ip != 0 && qp != 0 && pip != 0 && pqp != 0) {
-    k.cross = (long long)(ip * pqp - pip * qp);  // int products, as in the reference
-    long long dt = (long long)(ip * pip + qp * pqp);
-    k.dot = dt < 0 ? -dt : dt;
-    k.cross >>= 8;
-    k.dot >>= 8;
-    // operands: abs(cross), dot < 2^23 and abs(qp), abs(ip) <= 2^15 (shorts) -> the int32 form is exact
-    k.freqError = (long long)dev_atan2_i32((int)k.cross, (int)k.dot);
-    k.carrError = (long long)(dev_atan2_i32(qp * dev_sgn(ip), ip < 0 ? -ip : ip) / 2);
+    k.cross = (long long)cross8;
+    k.dot = (long long)dot8;
+    k.freqError = (long long)at_f;
+    k.carrError = (long long)(at_p / 2);
   } else {
     k.freqError = 0;
     k.carrError = k.oldCarrError;
@@ -257,12 +279,9 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
   k.carrFreq = k.carrFreqBasis + k.carrNco;
   dev_ch_carrier(r, c, k.carrFreq);
 
-  if (ie != 0 && qe != 0 && il != 0 && ql != 0) {
-    unsigned se = dev_isqrt((long long)(ie * ie + qe * qe)), sl = dev_isqrt((long long)(il * il + ql * ql));
-    // (8192*(se-sl))/(se+sl): se, sl <= 46341, so everything fits int32 (C division truncates toward zero)
-    const int num = 8192 * ((int)se - (int)sl);
-    k.codeError = (long long)dev_div_small(num, (int)se + (int)sl);  // abs(num) <= 2^29.5, den <= 92684, abs(q) <= 8192
-  } else
+  if (ie != 0 && qe != 0 && il != 0 && ql != 0)
+    k.codeError = (long long)code_q;
+  else
     k.codeError = k.oldCodeError;
   {
     const long long num = (c.dll_i1 + 1) * k.codeError - c.dll_i2 * k.oldCodeError;
@@ -275,7 +294,7 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
   dev_ch_code(r, c, k.codeFreq);
 }
 
-__device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+__device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   const int ip = k.accum[A_IP], pip = k.prev_accum[A_IP];
   dev_isr_loops(k, r, c);
   if (dev_sgn(ip) == -dev_sgn(pip)) {
@@ -311,7 +330,7 @@ __device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, con
   }
 }
 
-__device__ __forceinline__ void dev_isr_track(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+__device__ __forceinline__ void dev_isr_track(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   dev_isr_loops(k, r, c);
   k.ms_count = (k.ms_count + 1) % 20;
   if (k.ms_count == 19) k.bit = k.accum[A_IP] > 0 ? 1 : 0;
@@ -319,7 +338,7 @@ __device__ __forceinline__ void dev_isr_track(gnssb200_chan &k, ChRegs &r, const
 
 // One channel's share of gpsisr() for a block in which it dumped.  Returns 1 on CHANNEL_OFF (the
 // reference exit(0)s there).
-__device__ __forceinline__ int dev_gpsisr_channel(gnssb200_chan &k, ChRegs &r, const gnssb200_cfg &c) {
+__device__ __forceinline__ int dev_gpsisr_channel(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
 #pragma unroll
   for (int a = 0; a < 6; a++) k.prev_accum[a] = k.accum[a];
   k.accum[A_IE] = (int16_t)r.r_acc[4];  // from_gps(): short

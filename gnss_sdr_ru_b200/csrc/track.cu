@@ -61,7 +61,7 @@ struct TrackArgs {
   gnssb200_dump *dumps;
   int dump_cap;
   int32_t *dump_count;
-  gnssb200_cfg cfg;
+  DevCfg cfg;
 };
 
 // byte k of w, sign extended, in one PRMT: selector nibble k copies the byte, nibble k|8 replicates
@@ -956,6 +956,44 @@ __global__ void track_finish_kernel(gnssb200_rx *rx, const int32_t *chan_flags, 
   if (halted) r->halted = 1;
 }
 
+// ---- diagnostics: the device ISR's integer helpers on arrays (tests/test_isr_math.py) -----------------
+__global__ void isr_math_kernel(int n, const int *y, const int *x, int *at, const long long *L, unsigned *sq, const int *num,
+                                const int *den, int *dv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  at[i] = dev_atan2_i32(y[i], x[i]);
+  sq[i] = dev_isqrt(L[i]);
+  dv[i] = dev_div_small(num[i], den[i]);
+}
+
+extern "C" int gnssb200_isr_math_eval(gnssb200_handle *h, int n, const int32_t *y, const int32_t *x, int32_t *atan_out,
+                                      const int64_t *L, uint32_t *sqrt_out, const int32_t *num, const int32_t *den,
+                                      int32_t *div_out) {
+  if (!h || n <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int *d_i = nullptr;
+  long long *d_L = nullptr;
+  CUDA_TRY(cudaMalloc(&d_i, (size_t)n * 7 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&d_L, (size_t)n * sizeof(long long)));
+  int *dy = d_i, *dx = d_i + n, *dat = d_i + 2 * (size_t)n, *dnum = d_i + 3 * (size_t)n, *dden = d_i + 4 * (size_t)n,
+      *ddv = d_i + 5 * (size_t)n;
+  unsigned *dsq = (unsigned *)(d_i + 6 * (size_t)n);
+  CUDA_TRY(cudaMemcpy(dy, y, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dnum, num, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dden, den, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_L, L, (size_t)n * 8, cudaMemcpyHostToDevice));
+  isr_math_kernel<<<(n + 255) / 256, 256>>>(n, dy, dx, dat, d_L, dsq, dnum, dden, ddv);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(atan_out, dat, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(sqrt_out, dsq, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(div_out, ddv, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_i);
+  cudaFree(d_L);
+  h->launches += 1;
+  return 0;
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 void build_code_table_host(uint32_t *table) {
   // C/A Gold codes, G2 register start states per PRN (IS-GPS-200; same values as correlator.c:67-71),
@@ -1000,7 +1038,12 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   a.dumps = d_dumps;
   a.dump_cap = dump_cap;
   a.dump_count = d_dump_count;
-  a.cfg = h->cfg;
+  static_cast<gnssb200_cfg &>(a.cfg) = h->cfg;
+  {
+    const double m = h->cfg.clock_mult;
+    const long long im = (long long)m;
+    a.cfg.mult_i = ((double)im == m && im > -1024 && im < 1024) ? (int)im : 0;
+  }
   const int grid = n_streams * NCH;
   static int env_spt = -1;
   if (env_spt < 0) {

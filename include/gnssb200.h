@@ -187,6 +187,16 @@ int64_t gnssb200_launch_count(const gnssb200_handle *h);
  * sequence; valid after the stream was synchronised. */
 float gnssb200_last_kernel_ms(gnssb200_handle *h);
 
+/* Diagnostics: evaluates the device ISR's integer helpers element-wise on host arrays of length n:
+ *   atan_out[i] = fix_atan2(y[i], x[i])            OSG/isr/osgpsisr.c:199-231 (int32 operands)
+ *   sqrt_out[i] = sqrt_newton(L[i])                 osgpsisr.c:148-178
+ *   div_out[i]  = num[i] / den[i] (C truncation)    the DLL discriminator division, osgpsisr.c:586,743
+ *                 for abs(num) < 2^30, 0 < den < 2^20
+ * so tests can compare them with the reference's own helpers on arbitrary arguments. */
+int gnssb200_isr_math_eval(gnssb200_handle *h, int n, const int32_t *y, const int32_t *x, int32_t *atan_out,
+                           const int64_t *L, uint32_t *sqrt_out, const int32_t *num, const int32_t *den,
+                           int32_t *div_out);
+
 /* ---------------------------------------------------------------------------------------------
  * synthetic IF records generated on the device (bench / test input, not part of the hot path).
  * Signal model of SIM/glonass_l3_generator.sce:60-186 + AWGN: per emitter
