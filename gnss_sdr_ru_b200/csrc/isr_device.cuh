@@ -8,6 +8,14 @@
 // Channels only touch their own registers, so each channel's lane owns a private register view.
 #pragma once
 #include "common.cuh"
+#ifdef TRACK_PROFILE  // cycle stamps of the ISR lane's sections (build with EXTRA_NVCC_FLAGS=-DTRACK_PROFILE)
+__device__ long long g_isr_t[8];
+#define ISR_STAMP(i) { long long _c = clock64(); g_isr_t[i] += _c - _t0; _t0 = _c; }
+#define ISR_T0 long long _t0 = clock64();
+#else
+#define ISR_STAMP(i)
+#define ISR_T0
+#endif
 
 
 // The slice of REG_write / REG_read that belongs to one channel.
@@ -97,18 +105,28 @@ __device__ __noinline__ unsigned dev_isqrt_newton(long long L) {
     }
   }
 }
+// Branch-free cores: each returns a value that is exact whenever it leaves `bad` untouched, and sets
+// `bad` when its float estimate was not within +-1 (cannot happen for the documented ranges, but the
+// callers then recompute with the literal slow forms, so exactness never rests on a float error bound).
+// Keeping the checks out of line lets the five discriminator chains of one dump share a basic block.
+__device__ __forceinline__ unsigned core_isqrt31(unsigned l, bool &bad) {  // 0 <= l < 2^31; 0 -> 0 (reference: L <= 0)
+  float sf;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"((float)l));
+  unsigned x = (unsigned)(sf + 0.5f);  // within +-1 of the answer; x <= 46342, so x*(x+1) < 2^32
+  x = x == 0 ? 1u : x;
+  x -= (x * (x - 1) > l) ? 1u : 0u;
+  x += ((x + 1) * x <= l) ? 1u : 0u;
+  bad |= (x * (x - 1) > l) | ((x + 1) * x <= l);
+  return l == 0 ? 0u : x;
+}
 __device__ __forceinline__ unsigned dev_isqrt(long long L) {
   if (L <= 0) return 0;
   if (L < (1ll << 31)) {
-    const unsigned l = (unsigned)L;
-    float sf;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"((float)l));
-    unsigned x = (unsigned)(sf + 0.5f);  // within +-1 of the answer; x <= 46342, so x*(x+1) < 2^32
-    x = x == 0 ? 1u : x;
-    x -= (x * (x - 1) > l) ? 1u : 0u;
-    x += ((x + 1) * x <= l) ? 1u : 0u;
-    if (x * (x - 1) > l || (x + 1) * x <= l) {  // never taken if the estimate is within +-1; keeps the result exact regardless
-      while (x * (x - 1) > l) x--;
+    bool bad = false;
+    unsigned x = core_isqrt31((unsigned)L, bad);
+    if (bad) {
+      const unsigned l = (unsigned)L;
+      x = 1;
       while ((x + 1) * x <= l) x++;
     }
     return x;
@@ -121,33 +139,24 @@ __device__ __forceinline__ unsigned dev_isqrt(long long L) {
 __device__ __forceinline__ int dev_atan2_n3(int n) {  // ((((n*n)>>14)*n)>>13)/9 with abs(n) <= 2^14
   return ((((n * n) >> 14) * n) >> 13) / 9;
 }
-// trunc((a << 14) / B) for 0 <= a <= B, 0 < B < 2^31 (so the quotient is <= 2^14): float estimate
-// (error < 1) corrected once in each direction with the exact remainder; a verified slow path keeps
-// the result exact whatever the estimate was.
-__device__ __forceinline__ unsigned dev_udiv_q14(unsigned a, unsigned B) {
+// trunc((a << 14) / B) for 0 <= a <= B, 0 < B < 2^30 (so the quotient is <= 2^14): float estimate
+// (error < 1) corrected once in each direction with the exact remainder.
+__device__ __forceinline__ unsigned core_udiv_q14(unsigned a, unsigned B, bool &bad) {
   unsigned q = (unsigned)__fdividef((float)a * 16384.0f, (float)B);
-  if (B < (1u << 30)) {
-    // true remainder lies in (-B, 2B), inside int32: wrapping 32-bit arithmetic recovers it exactly
-    int rem = (int)((a << 14) - q * B);
-    const bool lo = rem < 0;
-    q -= lo ? 1u : 0u;
-    rem += lo ? (int)B : 0;
-    const bool hi = rem >= (int)B;
-    q += hi ? 1u : 0u;
-    rem -= hi ? (int)B : 0;
-    if (rem < 0 || rem >= (int)B) q = (unsigned)(((unsigned long long)a << 14) / B);
-    return q;
-  }
-  return (unsigned)(((unsigned long long)a << 14) / B);
-}
-__device__ __forceinline__ int dev_div_q14(int y, int x) {  // trunc((y << 14) / x), abs(y) <= abs(x), x != 0
-  const unsigned ay = (unsigned)(y < 0 ? -y : y), B = (unsigned)(x < 0 ? -x : x);
-  const unsigned q = dev_udiv_q14(ay, B);
-  return ((y < 0) != (x < 0)) ? -(int)q : (int)q;
+  // true remainder lies in (-B, 2B), inside int32: wrapping 32-bit arithmetic recovers it exactly
+  int rem = (int)((a << 14) - q * B);
+  const bool lo = rem < 0;
+  q -= lo ? 1u : 0u;
+  rem += lo ? (int)B : 0;
+  const bool hi = rem >= (int)B;
+  q += hi ? 1u : 0u;
+  rem -= hi ? (int)B : 0;
+  bad |= (rem < 0) | (rem >= (int)B) | (B >= (1u << 30));
+  return q;
 }
 
 // trunc(num / den) for abs(num) < 2^30, 0 < den < 2^20 and abs(quotient) < 2^20 (C semantics: toward zero)
-__device__ __forceinline__ int dev_div_small(int num, int den) {
+__device__ __forceinline__ int core_div_small(int num, int den, bool &bad) {
   const unsigned an = (unsigned)(num < 0 ? -num : num);
   unsigned q = (unsigned)__fdividef((float)an, (float)den);
   int rem = (int)(an - q * (unsigned)den);
@@ -157,8 +166,13 @@ __device__ __forceinline__ int dev_div_small(int num, int den) {
   const bool hi = rem >= den;
   q += hi ? 1u : 0u;
   rem -= hi ? den : 0;
-  if (rem < 0 || rem >= den) q = an / (unsigned)den;
+  bad |= (rem < 0) | (rem >= den);
   return num < 0 ? -(int)q : (int)q;
+}
+__device__ __forceinline__ int dev_div_small(int num, int den) {
+  bool bad = false;
+  const int q = core_div_small(num, den, bad);
+  return bad ? num / den : q;
 }
 
 // fix_atan2() for arguments that fit int32 (always the case for the dumps of the reference: they are
@@ -168,18 +182,33 @@ __device__ __forceinline__ int dev_div_small(int num, int den) {
 //   x <= 0, -x >= abs(y): n = (y<<14)/x,  n - n3 (+pi if y > 0, else -pi)
 //   y > 0, y > abs(x):    n = (x<<14)/y,  pi/2 - n + n3
 //   y < 0, -y > abs(x):   n = (x<<14)/y,  -n + n3 - pi/2
-__device__ __forceinline__ int dev_atan2_i32(int y, int x) {
+__device__ __forceinline__ int atan2_from_quotient(int y, int x, bool horiz, unsigned q) {
   const int half_pi = 25736, pi = 51472;
-  const unsigned ay = (unsigned)(y < 0 ? -y : y), ax = (unsigned)(x < 0 ? -x : x);
-  const bool horiz = ax >= ay;  // cases 1, 2 (and x == y == 0)
-  const unsigned num = horiz ? ay : ax, den = horiz ? ax : ay;
-  const unsigned q = dev_udiv_q14(num, den == 0 ? 1u : den);
   const int n = ((y < 0) != (x < 0)) ? -(int)q : (int)q;
   const int t = n - dev_atan2_n3(n);
   const int rh = x > 0 ? t : (y > 0 ? t + pi : t - pi);
   const int rv = y > 0 ? half_pi - t : -t - half_pi;
   const int res = horiz ? rh : rv;
-  return (ax | ay) == 0 ? 0 : res;
+  return (x | y) == 0 ? 0 : res;
+}
+__device__ __forceinline__ int core_atan2_i32(int y, int x, bool &bad) {
+  const unsigned ay = (unsigned)(y < 0 ? -y : y), ax = (unsigned)(x < 0 ? -x : x);
+  const bool horiz = ax >= ay;  // cases 1, 2 (and x == y == 0)
+  const unsigned num = horiz ? ay : ax, den = horiz ? ax : ay;
+  const unsigned q = core_udiv_q14(num, den == 0 ? 1u : den, bad);
+  return atan2_from_quotient(y, x, horiz, q);
+}
+__device__ __noinline__ int dev_atan2_i32_slow(int y, int x) {  // same, the division done in 64 bits
+  const unsigned ay = (unsigned)(y < 0 ? -y : y), ax = (unsigned)(x < 0 ? -x : x);
+  const bool horiz = ax >= ay;
+  const unsigned num = horiz ? ay : ax, den = horiz ? ax : ay;
+  const unsigned q = (unsigned)(((unsigned long long)num << 14) / (den == 0 ? 1u : den));
+  return atan2_from_quotient(y, x, horiz, q);
+}
+__device__ __forceinline__ int dev_atan2_i32(int y, int x) {
+  bool bad = false;
+  const int r = core_atan2_i32(y, x, bad);
+  return bad ? dev_atan2_i32_slow(y, x) : r;
 }
 
 // indices into gnssb200_chan.accum[]
@@ -246,6 +275,7 @@ __device__ __forceinline__ void dev_isr_confirm(gnssb200_chan &k, ChRegs &r, con
 __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   const int ip = k.accum[A_IP], qp = k.accum[A_QP], pip = k.prev_accum[A_IP], pqp = k.prev_accum[A_QP];
   const int ie = k.accum[A_IE], qe = k.accum[A_QE], il = k.accum[A_IL], ql = k.accum[A_QL];
+  ISR_T0
   // The four discriminator primitives are evaluated up front and unconditionally (they are branch-free
   // and total), so their dependency chains interleave on the single ISR lane; the reference's
   // conditions select the results below.
@@ -253,50 +283,69 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
   const int dt = ip * pip + qp * pqp;
   const int dot8 = (int)((dt < 0 ? 0u - (unsigned)dt : (unsigned)dt) >> 8);  // abs() of the widened value, as the reference
   // operands: abs(cross), dot < 2^23 and abs(qp), abs(ip) <= 2^15 (shorts) -> the int32 form is exact
-  const int at_f = dev_atan2_i32(cross8, dot8);
-  const int at_p = dev_atan2_i32(qp * dev_sgn(ip), ip < 0 ? -ip : ip);
-  const unsigned se = dev_isqrt((long long)(ie * ie + qe * qe)), sl = dev_isqrt((long long)(il * il + ql * ql));
+  bool bad = false;
+  int at_f = core_atan2_i32(cross8, dot8, bad);
+  const int py = qp * dev_sgn(ip), px = ip < 0 ? -ip : ip;
+  int at_p = core_atan2_i32(py, px, bad);
+  const int Le = ie * ie + qe * qe, Ll = il * il + ql * ql;  // <= 2^31: a wrapped (negative) sum gives 0 like the reference
+  unsigned se = core_isqrt31(Le < 0 ? 0u : (unsigned)Le, bad), sl = core_isqrt31(Ll < 0 ? 0u : (unsigned)Ll, bad);
   // (8192*(se-sl))/(se+sl): se, sl <= 46341, so everything fits int32 (C division truncates toward zero)
-  const int den_c = (int)se + (int)sl;
-  const int code_q = dev_div_small(8192 * ((int)se - (int)sl), den_c > 0 ? den_c : 1);  // abs(num) <= 2^29.5, den <= 92684, abs(q) <= 8192
-
-  if (ip != 0 && qp != 0 && pip != 0 && pqp != 0) {
+  int den_c = (int)se + (int)sl;
+  int code_q = core_div_small(8192 * ((int)se - (int)sl), den_c > 0 ? den_c : 1, bad);  // abs(num) <= 2^29.5, den <= 92684, abs(q) <= 8192
+  if (bad) {  // an estimate was off by more than one (not expected): literal forms
+    at_f = dev_atan2_i32_slow(cross8, dot8);
+    at_p = dev_atan2_i32_slow(py, px);
+    se = dev_isqrt((long long)Le);
+    sl = dev_isqrt((long long)Ll);
+    den_c = (int)se + (int)sl;
+    code_q = (8192 * ((int)se - (int)sl)) / (den_c > 0 ? den_c : 1);
+  }
+  ISR_STAMP(0)
+  const bool carr_ok = ip != 0 && qp != 0 && pip != 0 && pqp != 0;
+  const long long oce = k.oldCarrError, ode = k.oldCodeError;
+  const long long ce = carr_ok ? (long long)(at_p / 2) : oce;
+  const long long fe = carr_ok ? (long long)at_f : 0ll;
+  if (carr_ok) {
     k.cross = (long long)cross8;
     k.dot = (long long)dot8;
-    k.freqError = (long long)at_f;
-    k.carrError = (long long)(at_p / 2);
-  } else {
-    k.freqError = 0;
-    k.carrError = k.oldCarrError;
   }
+  k.freqError = fe;
+  k.carrError = ce;
   {
-    const long long num = c.pll_i1 * k.carrError - c.pll_i2 * k.oldCarrError - c.pll_i3 * k.freqError;
+    // 32 x 32 -> 64-bit products when the carried-over error is an int32 (it always is: it came from fix_atan2)
+    const long long num = (oce == (long long)(int)oce)
+                              ? (long long)c.pll_i1 * (int)ce - (long long)c.pll_i2 * (int)oce - (long long)c.pll_i3 * (int)fe
+                              : c.pll_i1 * ce - c.pll_i2 * oce - c.pll_i3 * fe;
     const long long q = (num == (long long)(int)num) ? (long long)((int)num / 51472) : num / 51472;
     k.carrNco = k.oldCarrNco + q;
   }
   k.oldCarrNco = k.carrNco;
-  k.oldCarrError = k.carrError;
+  k.oldCarrError = ce;
   k.carrFreq = k.carrFreqBasis + k.carrNco;
+  ISR_STAMP(1)
   dev_ch_carrier(r, c, k.carrFreq);
+  ISR_STAMP(2)
 
-  if (ie != 0 && qe != 0 && il != 0 && ql != 0)
-    k.codeError = (long long)code_q;
-  else
-    k.codeError = k.oldCodeError;
+  const long long de = (ie != 0 && qe != 0 && il != 0 && ql != 0) ? (long long)code_q : ode;
+  k.codeError = de;
   {
-    const long long num = (c.dll_i1 + 1) * k.codeError - c.dll_i2 * k.oldCodeError;
+    const long long num = (ode == (long long)(int)ode) ? (long long)(c.dll_i1 + 1) * (int)de - (long long)c.dll_i2 * (int)ode
+                                                       : (c.dll_i1 + 1) * de - c.dll_i2 * ode;
     const long long q = (num == (long long)(int)num) ? (long long)((int)num / 8192) : num / 8192;
     k.codeNco = k.oldCodeNco + q;
   }
   k.oldCodeNco = k.codeNco;
-  k.oldCodeError = k.codeError;
+  k.oldCodeError = de;
   k.codeFreq = k.codeFreqBasis - k.codeNco;
+  ISR_STAMP(3)
   dev_ch_code(r, c, k.codeFreq);
+  ISR_STAMP(4)
 }
 
 __device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   const int ip = k.accum[A_IP], pip = k.prev_accum[A_IP];
   dev_isr_loops(k, r, c);
+  ISR_T0
   if (dev_sgn(ip) == -dev_sgn(pip)) {
     k.prev_sign_pos = k.sign_pos;
     k.sign_pos = (int)k.ch_time;
@@ -328,6 +377,7 @@ __device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, con
     k.ch_time = 0;
     k.state = 1;
   }
+  ISR_STAMP(5)
 }
 
 __device__ __forceinline__ void dev_isr_track(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
