@@ -342,9 +342,18 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
   ISR_STAMP(4)
 }
 
-__device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
-  const int ip = k.accum[A_IP], pip = k.prev_accum[A_IP];
+// Pull-in and tracking are split in two: the part that decides the channel's NCO words (what the next
+// block's correlator parameters depend on) and the bookkeeping that only touches the channel struct, so
+// the kernel can publish the next block's parameters before the bookkeeping runs.
+__device__ __forceinline__ void dev_isr_pull_in_words(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   dev_isr_loops(k, r, c);
+  if (k.ch_time + 1 == 3000) {  // the time-out below will reload the reference words
+    dev_ch_carrier(r, c, c.gps_carrier_ref);
+    dev_ch_code(r, c, c.gps_code_ref);
+  }
+}
+__device__ __forceinline__ void dev_isr_pull_in_rest(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
+  const int ip = k.accum[A_IP], pip = k.prev_accum[A_IP];
   ISR_T0
   if (dev_sgn(ip) == -dev_sgn(pip)) {
     k.prev_sign_pos = k.sign_pos;
@@ -371,7 +380,7 @@ __device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, con
   if (k.ch_time == 3000) {
     k.del_freq = 1;
     k.n_freq = 0;
-    dev_ch_carrier(r, c, c.gps_carrier_ref);
+    dev_ch_carrier(r, c, c.gps_carrier_ref);  // same words as dev_isr_pull_in_words wrote
     dev_ch_code(r, c, c.gps_code_ref);
     k.codes = 0;
     k.ch_time = 0;
@@ -380,15 +389,15 @@ __device__ __forceinline__ void dev_isr_pull_in(gnssb200_chan &k, ChRegs &r, con
   ISR_STAMP(5)
 }
 
-__device__ __forceinline__ void dev_isr_track(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
-  dev_isr_loops(k, r, c);
+__device__ __forceinline__ void dev_isr_track_rest(gnssb200_chan &k) {
   k.ms_count = (k.ms_count + 1) % 20;
   if (k.ms_count == 19) k.bit = k.accum[A_IP] > 0 ? 1 : 0;
 }
 
-// One channel's share of gpsisr() for a block in which it dumped.  Returns 1 on CHANNEL_OFF (the
-// reference exit(0)s there).
-__device__ __forceinline__ int dev_gpsisr_channel(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
+// One channel's share of gpsisr() for a block in which it dumped, first part: the new dump values and
+// everything that can change the channel's write registers (NCO words, slew).  state_in receives the
+// state the dump was handled in.  Returns 1 on CHANNEL_OFF (the reference exit(0)s there).
+__device__ __forceinline__ int dev_gpsisr_words(gnssb200_chan &k, ChRegs &r, const DevCfg &c, int &state_in) {
 #pragma unroll
   for (int a = 0; a < 6; a++) k.prev_accum[a] = k.accum[a];
   k.accum[A_IE] = (int16_t)r.r_acc[4];  // from_gps(): short
@@ -397,13 +406,30 @@ __device__ __forceinline__ int dev_gpsisr_channel(gnssb200_chan &k, ChRegs &r, c
   k.accum[A_QP] = (int16_t)r.r_acc[3];
   k.accum[A_IL] = (int16_t)r.r_acc[0];
   k.accum[A_QL] = (int16_t)r.r_acc[1];
+  state_in = k.state;
   switch (k.state) {
     case 0: return 1;
     case 1: dev_isr_search(k, r, c); break;
-    case 2: dev_isr_confirm(k, r, c); break;
-    case 3: dev_isr_pull_in(k, r, c); break;
-    case 4: dev_isr_track(k, r, c); break;
+    case 3: dev_isr_pull_in_words(k, r, c); break;
+    case 4: dev_isr_loops(k, r, c); break;
     default: break;
   }
+  return 0;
+}
+// second part: bookkeeping on the channel struct (and the epoch-load request of the bit sync)
+__device__ __forceinline__ void dev_gpsisr_rest(gnssb200_chan &k, ChRegs &r, const DevCfg &c, int state_in) {
+  switch (state_in) {
+    case 2: dev_isr_confirm(k, r, c); break;
+    case 3: dev_isr_pull_in_rest(k, r, c); break;
+    case 4: dev_isr_track_rest(k); break;
+    default: break;
+  }
+}
+
+// Both parts back to back (the order of the reference).
+__device__ __forceinline__ int dev_gpsisr_channel(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
+  int st;
+  if (dev_gpsisr_words(k, r, c, st)) return 1;
+  dev_gpsisr_rest(k, r, c, st);
   return 0;
 }

@@ -325,7 +325,19 @@ struct ChanShared {
   int dump_count;
 };
 
-__device__ __forceinline__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+// epoch-counter load request of the host logic, applied at the start of a block (correlator.c:177-182)
+__device__ __forceinline__ void apply_epoch_load(ChanShared &cs) {
+  ChRegs &r = cs.r;
+  if (r.w_epoch != -1) {
+    r.r_meas[7] = r.w_epoch;
+    cs.g.ms_counter = r.w_epoch & 0xff;
+    cs.g.bit_counter = r.w_epoch >> 8;
+    r.w_epoch = -1;
+  }
+}
+
+// correlator parameters of the next block from the channel's registers and correlator state
+__device__ __forceinline__ void prepare_block_params(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
   const long long n = a.nsamp;
   if (cs.tic < n) {  // correlator.c:155-165
     sp.tic_count = (int)cs.tic;
@@ -338,12 +350,6 @@ __device__ __forceinline__ void prepare_block(ChanShared &cs, StepParams &sp, co
   sp.cyc_pending = 0;
   ChRegs &r = cs.r;
   gnssb200_corr &g = cs.g;
-  if (r.w_epoch != -1) {  // :177-182
-    r.r_meas[7] = r.w_epoch;
-    g.ms_counter = r.w_epoch & 0xff;
-    g.bit_counter = r.w_epoch >> 8;
-    r.w_epoch = -1;
-  }
   if (r.w_prn <= 0) {
     sp.mode = MODE_IDLE;
     return;
@@ -363,6 +369,11 @@ __device__ __forceinline__ void prepare_block(ChanShared &cs, StepParams &sp, co
               (long long)wtot < w1 + slew_dump && (sp.hc0 + wtot + 40) < SMEM_TBL && (sp.hc0 + w1) < SMEM_TBL &&
               n < (1ll << 30) && sp.kinc >= 1u && sp.kinc < (1u << 30);
   sp.mode = fast ? MODE_FAST : MODE_SERIAL;
+}
+
+__device__ __forceinline__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+  apply_epoch_load(cs);
+  prepare_block_params(cs, sp, a, tbl_prn);
 }
 
 // dump side effects common to both paths (correlator.c:252-281)
@@ -927,6 +938,406 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   }
 }
 
+// ==================================================================================================
+// Warp-specialised variant of the channel loop (the hot path for 8192-sample TMA-staged blocks).
+//
+// Eight correlator warps and one control lane per (stream, channel) CTA, decoupled by mbarriers:
+//
+//   control lane    issues the TMA load of block b+1, derives the parameters of block b+1 (closed
+//                   forms for quiet blocks; reduction totals -> dump rules -> channel state machine
+//                   for event blocks) and publishes them in a two-slot ring; the bookkeeping part of
+//                   the ISR (bit sync, confirm counters, the dump record) runs AFTER the publish, while
+//                   the correlator warps already work on the next block.
+//   correlator warp waits for parameters + samples of block b, correlates its 8 x 32 x 32 samples,
+//                   carries its sums in registers over quiet blocks; in an event block it reduces
+//                   (REDUX.SUM) into shared-memory totals and signals the control lane.  No CTA-wide
+//                   barrier in the loop; a warp is at most one block ahead of the slowest one.
+//
+// Same arithmetic, same rules, same results as track_loop_kernel (which remains the generic variant).
+struct __align__(16) BlockParams {
+  uint32_t cph0, kph0, cinc, kinc;
+  uint32_t hc0, w1, stale_idx, stale_bits;
+  int mode, event, pad0, pad1;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// Is block `sp` an event block (reduce + control-lane work at its end)?  If not, nx = parameters of the
+// next block from the closed forms.  Same rule as the quiet test of track_loop_kernel.
+__device__ __forceinline__ bool classify_block(const StepParams &sp, const TrackArgs &a, bool last, StepParams &nx) {
+  if (sp.mode != MODE_FAST || last) return true;
+  const unsigned long long n = (unsigned long long)a.nsamp;
+  const unsigned long long nk = n * sp.kinc, nc = n * sp.cinc;
+  const unsigned long long kend = (unsigned long long)sp.kph0 + nk;
+  const unsigned long long cend = (unsigned long long)sp.cph0 + nc;
+  const uint32_t wtot = (uint32_t)(kend >> 32);
+  nx = sp;
+  nx.kph0 = (uint32_t)kend;
+  nx.cph0 = (uint32_t)cend;
+  nx.hc0 = sp.hc0 + wtot;
+  nx.w1 = sp.w1 - wtot;
+  nx.cyc_pending = sp.cyc_pending + (uint32_t)(cend >> 32);
+  if (sp.tic < (long long)n) {
+    nx.tic_count = (int)sp.tic;
+    nx.tic = sp.tic + a.cfg.tic_ref - (long long)n;
+  } else {
+    nx.tic_count = -1;
+    nx.tic = sp.tic - (long long)n;
+  }
+  const unsigned long long wnext = ((unsigned long long)nx.kph0 + nk) >> 32;
+  const bool next_fast = wnext < (unsigned long long)nx.w1 + sp.slew_dump && (nx.hc0 + wnext + 40) < SMEM_TBL;
+  const bool quiet = wtot < sp.w1 && !(sp.tic_count >= 0 && sp.tic_count < a.nsamp) && next_fast;
+  return !quiet;
+}
+
+#define WS_CORR_THREADS 256
+#define WS_THREADS 288
+template <int MINB, int FMT>
+__global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackArgs a, const int tile_bytes) {
+  constexpr int SPT = 32;
+  constexpr int fmt = FMT;
+  constexpr bool packed_native = FMT == GNSSB200_FMT_PACKED2;
+  __shared__ ChanShared cs;
+  __shared__ BlockParams params[2];
+  __shared__ uint2 lut[8];
+  __shared__ uint32_t tbl[SMEM_TBL];
+  __shared__ uint32_t alias_tbl[2][48];  // per ring slot: tbl[0..47] with entry 0 = the block's stale bits (rule A6)
+  __shared__ __align__(16) int totals[12];
+  __shared__ __align__(8) uint64_t dfull[2], pfull[2], empty[2], tfull;
+  extern __shared__ __align__(128) uint8_t tiles[];
+  uint32_t *vlut = reinterpret_cast<uint32_t *>(tiles + 2 * (size_t)tile_bytes);
+
+  const int s = a.first_stream + blockIdx.x / NCH, ch = blockIdx.x % NCH;
+  gnssb200_rx *rx = a.rx + s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tbl_prn = rx->reg_write[ch << 3];
+  const size_t blk_bytes = bytes_for(fmt, a.nsamp);
+  const uint8_t *stream_base = a.d_if + (size_t)s * a.stride;
+  constexpr int CTRL = WS_CORR_THREADS;  // the control lane
+
+  fill_lo_lut(lut);
+  if (tid < 12) totals[tid] = 0;
+  for (int i = tid; i < SMEM_TBL; i += WS_THREADS) {
+    long long f = (long long)tbl_prn * HALF_CHIPS + i;
+    tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+  }
+  if (packed_native) {
+    const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
+    const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
+    const int val[4] = {1, -1, 3, -3};
+    for (int i = tid; i < 128 * 32; i += WS_THREADS) {
+      const int e = i >> 5, ph = e >> 4, code = e & 15;
+      const int I = val[code & 3], Q = val[code >> 2];
+      const int ival = i_lo[ph] * I + q_lo[ph] * Q, qval = q_lo[ph] * I - i_lo[ph] * Q;  // correlator.c:214-215
+      vlut[i] = (uint32_t)(ival + 65536 * qval);
+    }
+  }
+  if (tid < 96) {
+    const int t = tid % 48;
+    long long f = (long long)tbl_prn * HALF_CHIPS + t;
+    alias_tbl[tid / 48][t] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+  }
+  __syncthreads();  // tbl complete before the control lane looks up stale bits
+  const int b8 = ch << 3;
+  StepParams sp;
+  long long first_block = 0;
+  long long loaded = -1;  // last block whose TMA load was issued
+  if (tid == CTRL) {
+    cs.k = rx->chan[ch];
+    cs.g = rx->corr[ch];
+    cs.r.w_prn = rx->reg_write[b8];
+    cs.r.w_carr_hi = rx->reg_write[b8 + 3];
+    cs.r.w_carr_lo = rx->reg_write[b8 + 4];
+    cs.r.w_code_hi = rx->reg_write[b8 + 5];
+    cs.r.w_code_lo = rx->reg_write[b8 + 6];
+    cs.r.w_epoch = rx->reg_write[b8 + 7];
+    cs.r.w_slew = rx->reg_write[b8 + 0x84];
+    for (int q = 0; q < 8; q++) cs.r.r_meas[q] = rx->reg_read[b8 + q];
+    for (int q = 0; q < 6; q++) cs.r.r_acc[q] = rx->reg_read[b8 + 0x84 + q];
+    cs.tic = rx->tic;
+    cs.dumped_last = 0;
+    cs.halted = 0;
+    cs.dump_count = a.dump_count ? a.dump_count[s * NCH + ch] : 0;
+    first_block = rx->blocks_done;
+    sp.stale_bits = 0;
+    if (a.nblocks > 0 && !rx->halted) {
+      prepare_block(cs, sp, a, tbl_prn);
+      if (sp.mode == MODE_FAST) sp.stale_bits = tbl[sp.stale_idx];
+    } else
+      sp.mode = MODE_STOP;
+    mbar_init(&dfull[0], 1);
+    mbar_init(&dfull[1], 1);
+    mbar_init(&pfull[0], 1);
+    mbar_init(&pfull[1], 1);
+    mbar_init(&empty[0], WS_CORR_THREADS / 32);
+    mbar_init(&empty[1], WS_CORR_THREADS / 32);
+    mbar_init(&tfull, WS_CORR_THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (sp.mode == MODE_FAST || sp.mode == MODE_SERIAL) {
+      mbar_expect_tx(&dfull[0], (uint32_t)blk_bytes);
+      tma_load_1d(tiles, stream_base, (uint32_t)blk_bytes, &dfull[0]);
+      loaded = 0;
+    }
+  }
+  __syncthreads();  // mbarriers initialised
+
+  // ---------------- control lane ----------------
+  if (warp == WS_CORR_THREADS / 32) {
+    if (lane != 0) return;
+    auto publish = [&](int slot, const StepParams &sp, bool event) {
+      BlockParams &p = params[slot];
+      p.cph0 = sp.cph0; p.kph0 = sp.kph0; p.cinc = sp.cinc; p.kinc = sp.kinc;
+      p.hc0 = sp.hc0; p.w1 = sp.w1; p.stale_idx = sp.stale_idx; p.stale_bits = sp.stale_bits;
+      p.mode = sp.mode; p.event = event ? 1 : 0;
+      alias_tbl[slot][0] = sp.stale_bits;
+      mbar_arrive(&pfull[slot]);  // release: the stores above are visible to whoever observes the phase
+    };
+    StepParams nx;
+    bool event = classify_block(sp, a, a.nblocks <= 1, nx);
+    publish(0, sp, event);
+    uint32_t ev_phase = 0;
+    for (long long b = 0; b < a.nblocks; b++) {
+      if (sp.mode == MODE_STOP) break;
+      const bool last = b + 1 == a.nblocks;
+      const int slot = (int)(b & 1), nslot = slot ^ 1;
+      if (!last) {
+        // ring slot of block b+1 (parameters, alias table, tile) is free once every warp finished block b-1
+        if (b >= 1) mbar_wait(&empty[nslot], (uint32_t)(((b - 1) >> 1) & 1));
+        if (sp.mode != MODE_IDLE) {
+          mbar_expect_tx(&dfull[nslot], (uint32_t)blk_bytes);
+          tma_load_1d(tiles + (size_t)nslot * tile_bytes, stream_base + (size_t)(b + 1) * blk_bytes, (uint32_t)blk_bytes, &dfull[nslot]);
+          loaded = b + 1;
+        }
+      }
+      if (!event) {  // quiet block: nothing leaves the correlator threads
+        sp = nx;
+        event = classify_block(sp, a, b + 2 == a.nblocks, nx);
+        publish(nslot, sp, event);
+        continue;
+      }
+      int A[6] = {0, 0, 0, 0, 0, 0}, B[6] = {0, 0, 0, 0, 0, 0};
+      if (sp.mode == MODE_FAST) {
+        mbar_wait(&tfull, ev_phase);
+        ev_phase ^= 1;
+        const int4 t0 = *reinterpret_cast<const int4 *>(&totals[0]);
+        const int4 t1 = *reinterpret_cast<const int4 *>(&totals[4]);
+        const int4 t2 = *reinterpret_cast<const int4 *>(&totals[8]);
+        A[0] = t0.x; A[1] = t0.y; A[2] = t0.z; A[3] = t0.w; A[4] = t1.x; A[5] = t1.y;
+        B[0] = t1.z; B[1] = t1.w; B[2] = t2.x; B[3] = t2.y; B[4] = t2.z; B[5] = t2.w;
+        const int4 z = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<int4 *>(&totals[0]) = z;  // the next event block's atomics come after the publish below
+        *reinterpret_cast<int4 *>(&totals[4]) = z;
+        *reinterpret_cast<int4 *>(&totals[8]) = z;
+      }
+      cs.tic = sp.tic;
+      cs.g.carrier_cycle += sp.cyc_pending;
+      if (sp.mode == MODE_FAST)
+        finalize_fast(cs, sp, A, B, a.nsamp);
+      else if (sp.mode == MODE_SERIAL) {
+        mbar_wait(&dfull[slot], (uint32_t)((b >> 1) & 1));
+        serial_block(cs, sp, a.code_table, fmt, a.nsamp, tiles + (size_t)slot * tile_bytes);
+      } else
+        cs.dumped_last = 0;
+      // ISR, first part: whatever can change the NCO words / slew
+      int st_in = -1;
+      bool isr = false;
+      if (cs.dumped_last && a.run_isr) {
+        if (dev_gpsisr_words(cs.k, cs.r, a.cfg, st_in))
+          cs.halted = 1;
+        else
+          isr = true;
+      }
+      const int was_mode = sp.mode;
+      if (cs.halted || was_mode == MODE_IDLE)  // an idle channel has no ISR: nothing can change any more
+        sp.mode = MODE_STOP;
+      else if (!last) {
+        prepare_block_params(cs, sp, a, tbl_prn);
+        sp.stale_bits = sp.mode == MODE_FAST ? tbl[sp.stale_idx] : 0u;
+      }
+      if (!last) {
+        event = classify_block(sp, a, b + 2 == a.nblocks, nx);
+        publish(nslot, sp, event);
+      }
+      // second part, off the correlators' critical path
+      if (isr) dev_gpsisr_rest(cs.k, cs.r, a.cfg, st_in);
+      if (cs.dumped_last && !cs.halted && a.dumps && cs.dump_count < a.dump_cap) {
+        gnssb200_dump *out = &a.dumps[((size_t)s * NCH + ch) * a.dump_cap + cs.dump_count];
+        int4 q0, q1, q2;
+        q0.x = (int)(first_block + b);
+        q0.y = (int)(uint16_t)(int16_t)ch | ((int)(uint16_t)(int16_t)cs.k.state << 16);
+        q0.z = cs.r.r_acc[0];
+        q0.w = cs.r.r_acc[1];
+        q1.x = cs.r.r_acc[2];
+        q1.y = cs.r.r_acc[3];
+        q1.z = cs.r.r_acc[4];
+        q1.w = cs.r.r_acc[5];
+        q2.x = (cs.r.w_carr_hi << 16) + cs.r.w_carr_lo;
+        q2.y = (cs.r.w_code_hi << 16) + cs.r.w_code_lo;
+        q2.z = (int)(uint16_t)(int16_t)cs.k.n_freq | ((int)(uint16_t)(int16_t)cs.k.codes << 16);
+        q2.w = cs.r.w_slew;
+        int4 *o4 = reinterpret_cast<int4 *>(out);
+        o4[0] = q0;
+        o4[1] = q1;
+        o4[2] = q2;
+        cs.dump_count++;
+      }
+      if (!last && sp.mode != MODE_STOP) apply_epoch_load(cs);  // start-of-block rule of the next block
+    }
+    // a prefetched block nobody consumed must land before the CTA may exit
+    if (loaded >= 0) mbar_wait(&dfull[loaded & 1], (uint32_t)((loaded >> 1) & 1));
+    rx->chan[ch] = cs.k;
+    rx->corr[ch] = cs.g;
+    rx->reg_write[b8 + 3] = cs.r.w_carr_hi;
+    rx->reg_write[b8 + 4] = cs.r.w_carr_lo;
+    rx->reg_write[b8 + 5] = cs.r.w_code_hi;
+    rx->reg_write[b8 + 6] = cs.r.w_code_lo;
+    rx->reg_write[b8 + 7] = cs.r.w_epoch;
+    rx->reg_write[b8 + 0x84] = cs.r.w_slew;
+    for (int q = 1; q < 8; q++) rx->reg_read[b8 + q] = cs.r.r_meas[q];
+    for (int q = 0; q < 6; q++) rx->reg_read[b8 + 0x84 + q] = cs.r.r_acc[q];
+    a.chan_flags[s * NCH + ch] = (cs.dumped_last ? 1 : 0) | (cs.halted ? 2 : 0);
+    if (a.dump_count) a.dump_count[s * NCH + ch] = cs.dump_count;
+    return;
+  }
+  (void)first_block;
+  (void)loaded;
+
+  // ---------------- correlator warps ----------------
+  const int i0 = tid * SPT;
+  const bool live = i0 < a.nsamp;
+  const uint32_t vlut_lane = smem_u32(vlut) + 4u * (uint32_t)lane;
+  int carry[6] = {0, 0, 0, 0, 0, 0};
+  for (long long b = 0; b < a.nblocks; b++) {
+    const int slot = (int)(b & 1);
+    const uint32_t par = (uint32_t)((b >> 1) & 1);
+    mbar_wait(&pfull[slot], par);
+    const uint4 p0 = reinterpret_cast<const uint4 *>(&params[slot])[0];
+    const uint4 p1 = reinterpret_cast<const uint4 *>(&params[slot])[1];
+    const int2 p2 = reinterpret_cast<const int2 *>(&params[slot])[4];
+    const int mode = p2.x;
+    const bool event = p2.y != 0;
+    if (mode == MODE_STOP) break;
+    if (mode == MODE_FAST) {
+      const uint32_t cph0 = p0.x, kph0 = p0.y, cinc = p0.z, kinc = p0.w;
+      const uint32_t hc0 = p1.x, w1 = p1.y, stale_idx = p1.z, stale_bits = p1.w;
+      const uint8_t *tile = tiles + (size_t)slot * tile_bytes;
+      mbar_wait(&dfull[slot], par);
+      int sumA[6] = {0, 0, 0, 0, 0, 0}, sumB[6] = {0, 0, 0, 0, 0, 0};
+      bool anyB = false;
+      {
+        uint32_t cur[SPT / 2];
+        uint32_t pk[SPT / 8];
+        if (live && packed_native) {
+          const uint32_t *pp = reinterpret_cast<const uint32_t *>(tile + (i0 >> 1));
+#pragma unroll
+          for (int q = 0; q < SPT / 8; q++) pk[q] = pp[q];
+        } else if (live) {
+          load_chunk<SPT, true>(tile, fmt, i0, a.nsamp, true, nullptr, cur);
+        }
+        const int i1 = live ? min(i0 + SPT, a.nsamp) : i0 + 1;
+        const unsigned long long k0 = (unsigned long long)kph0 + (unsigned long long)i0 * kinc;
+        const uint32_t w_start = (uint32_t)(k0 >> 32);
+        const uint32_t w_lastb = (uint32_t)(((unsigned long long)kph0 + (unsigned long long)(i1 - 1) * kinc) >> 32);
+        const bool allA = !live || w_lastb < w1, allB = live && w_start >= w1;
+        uint32_t h, hl;
+        if (allB) {
+          h = w_start - w1;
+          hl = (h == 0) ? stale_idx : h;  // stale bits after the dump (SURVEY.md App. A rule A6)
+        } else {
+          h = hc0 + w_start;
+          hl = h;
+        }
+        int pE = 0, pP = 0, pL = 0;
+        // chunk starting in the first post-dump half chip: stale bits first, then tbl[1], tbl[2], ...
+        const bool stale_start = allB && h == 0;
+        if (live && packed_native)
+          correlate_chunk_packed<SPT>(pk, cph0 + (uint32_t)i0 * cinc, (uint32_t)k0, cinc, kinc, stale_start ? alias_tbl[slot] : tbl, h,
+                                      stale_start ? stale_bits : tbl[hl], vlut_lane, pE, pP, pL);
+        else if (live)
+          correlate_chunk<SPT>(cur, cph0 + (uint32_t)i0 * cinc, (uint32_t)k0, cinc, kinc, stale_start ? alias_tbl[slot] : tbl, h,
+                               stale_start ? stale_bits : tbl[hl], lut, pE, pP, pL);
+        const bool straddle = !allA && !allB;
+        if (!straddle && live) {
+          int v[6];
+          unpack_lanes(pL, v[0], v[1]);
+          unpack_lanes(pP, v[2], v[3]);
+          unpack_lanes(pE, v[4], v[5]);
+          if (allA) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) sumA[q] += v[q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 6; q++) sumB[q] += v[q];
+          }
+        }
+        // the chunk that contains the dump is re-evaluated one sample per lane by its warp
+        unsigned m = __ballot_sync(0xffffffffu, straddle);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int si0 = __shfl_sync(0xffffffffu, i0, src);
+          for (int i = si0 + lane; i < min(si0 + SPT, a.nsamp); i += 32) {
+            const unsigned long long ki = (unsigned long long)kph0 + (unsigned long long)i * kinc;
+            const uint32_t wb = (uint32_t)(ki >> 32);
+            const bool inA = wb < w1;
+            const uint32_t rel = wb - w1;
+            const uint32_t hh = inA ? hc0 + wb : (rel == 0 ? stale_idx : rel);
+            const uint32_t t = tbl[hh];
+            int I, Q;
+            load_sample(tile, fmt, i, I, Q);
+            const uint2 ab = lut[(cph0 + (uint32_t)i * cinc) >> 29];
+            const int v = I * (int)ab.x + Q * (int)ab.y;
+            int vi, vq;
+            unpack_lanes(v, vi, vq);
+            const int cE = sext8(t, 0), cP = sext8(t, 1), cL = sext8(t, 2);
+            if (inA) {
+              sumA[0] += cL * vi; sumA[1] += cL * vq; sumA[2] += cP * vi;
+              sumA[3] += cP * vq; sumA[4] += cE * vi; sumA[5] += cE * vq;
+            } else {
+              sumB[0] += cL * vi; sumB[1] += cL * vq; sumB[2] += cP * vi;
+              sumB[3] += cP * vq; sumB[4] += cE * vi; sumB[5] += cE * vq;
+            }
+          }
+        }
+        anyB |= !allA;
+      }
+      if (!event) {  // no dump in this block: every chunk was pre-dump, keep the sums in registers
+#pragma unroll
+        for (int q = 0; q < 6; q++) carry[q] += sumA[q];
+      } else {
+        const bool warpB = __any_sync(0xffffffffu, anyB);
+        int va = 0, vb = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          const int ra = warp_sum(sumA[q] + carry[q]);
+          carry[q] = 0;
+          if (lane == q) va = ra;
+        }
+        if (warpB) {
+#pragma unroll
+          for (int q = 0; q < 6; q++) {
+            const int rb = warp_sum(sumB[q]);
+            if (lane == q) vb = rb;
+          }
+        }
+        if (lane < 6) {
+          atomicAdd(&totals[lane], va);
+          if (warpB) atomicAdd(&totals[6 + lane], vb);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (event && mode == MODE_FAST) mbar_arrive(&tfull);
+      mbar_arrive(&empty[slot]);
+    }
+  }
+}
+
 // one thread per stream: status words, TIC counter and block counter after a run
 __global__ void track_finish_kernel(gnssb200_rx *rx, const int32_t *chan_flags, int first_stream, int n_streams,
                                     int nsamp, long long nblocks, long long tic_ref) {
@@ -1088,6 +1499,30 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const bool dense = force_occ ? (force_occ >= 4) : (grid > 3 * sms);
   const bool hot = use_tma && threads <= 256 && (fmt == GNSSB200_FMT_INT8_IQ || fmt == GNSSB200_FMT_PACKED2);
+  static int use_ws = -1;
+  if (use_ws < 0) {
+    const char *e = getenv("GNSSB200_TRACK_WS");
+    use_ws = e ? atoi(e) : 1;
+  }
+  if (use_ws && hot && spt == 32) {  // warp-specialised variant: 8 correlator warps + control lane
+    static bool aws = false;
+    if (!aws) {
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_INT8_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
+      aws = true;
+    }
+    const bool dense_ws = force_occ ? (force_occ >= 3) : (grid > 2 * sms);
+    if (fmt == GNSSB200_FMT_INT8_IQ && dense_ws)
+      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+    else if (fmt == GNSSB200_FMT_INT8_IQ)
+      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+    else if (dense_ws)
+      track_ws_kernel<3, GNSSB200_FMT_PACKED2><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+    else
+      track_ws_kernel<2, GNSSB200_FMT_PACKED2><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+  } else
   if (spt == 16 && use_tma && fmt == GNSSB200_FMT_PACKED2) {  // experiment: 512 threads x 16 samples
     static bool a16 = false;
     if (!a16) {
