@@ -8,7 +8,7 @@
 // Channels only touch their own registers, so each channel's lane owns a private register view.
 #pragma once
 #include "common.cuh"
-#ifdef TRACK_PROFILE  // cycle stamps of the ISR lane's sections (build with EXTRA_NVCC_FLAGS=-DTRACK_PROFILE)
+#ifdef TRACK_PROFILE_ISR  // cycle stamps of the ISR lane's sections (build with EXTRA_NVCC_FLAGS="-DTRACK_PROFILE -DTRACK_PROFILE_ISR")
 __device__ long long g_isr_t[8];
 #define ISR_STAMP(i) { long long _c = clock64(); g_isr_t[i] += _c - _t0; _t0 = _c; }
 #define ISR_T0 long long _t0 = clock64();
@@ -36,6 +36,7 @@ __device__ __forceinline__ int reg16(int v) { return (int)(uint16_t)v; }  // out
 // Receiver constants plus what the device ISR derives from them once per launch (host side, track_launch).
 struct DevCfg : gnssb200_cfg {
   int mult_i;  // clock_mult when it is an integer in (-1024, 1024), else 0
+  int fast32;  // 1: the straight-line 32-bit form of the loop filters / NCO words applies (see dev_isr_loops)
 };
 
 __device__ __forceinline__ void dev_put_nco(int &hi, int &lo, long long freq, int bits, const DevCfg &c) {
@@ -292,6 +293,48 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
   // (8192*(se-sl))/(se+sl): se, sl <= 46341, so everything fits int32 (C division truncates toward zero)
   int den_c = (int)se + (int)sl;
   int code_q = core_div_small(8192 * ((int)se - (int)sl), den_c > 0 ? den_c : 1, bad);  // abs(num) <= 2^29.5, den <= 92684, abs(q) <= 8192
+  const bool carr_ok = ip != 0 && qp != 0 && pip != 0 && pqp != 0;
+  const bool code_ok = ie != 0 && qe != 0 && il != 0 && ql != 0;
+  const long long oce = k.oldCarrError, ode = k.oldCodeError;
+  // Straight-line 32-bit form of both loop filters and both NCO words.  Valid when the carried-over errors
+  // are small (they came out of fix_atan2 / the DLL discriminator: abs < 2^17), the filter coefficients keep
+  // the numerators inside int32 (c.fast32, checked on the host: abs(e) < 2^17, abs(f) < 2^16, abs(codeError)
+  // < 2^17), the clock multiplier is a small integer and the new frequencies fit int32 (checked below).
+  if (c.fast32 && !bad && (unsigned long long)(oce + (1ll << 17)) < (1ull << 18) && (unsigned long long)(ode + (1ll << 17)) < (1ull << 18)) {
+    const int e = carr_ok ? at_p / 2 : (int)oce;
+    const int f = carr_ok ? at_f : 0;
+    const int numc = c.pll_i1 * e - c.pll_i2 * (int)oce - c.pll_i3 * f;
+    const long long carrNco = k.oldCarrNco + (long long)(numc / 51472);
+    const long long carrFreq = k.carrFreqBasis + carrNco;
+    const int d = code_ok ? code_q : (int)ode;
+    const int numk = (c.dll_i1 + 1) * d - c.dll_i2 * (int)ode;
+    const long long codeNco = k.oldCodeNco + (long long)(numk / 8192);
+    const long long codeFreq = k.codeFreqBasis - codeNco;
+    if (carrFreq == (long long)(int)carrFreq && codeFreq == (long long)(int)codeFreq) {
+      const unsigned wc = ((unsigned)(int)carrFreq << (32 - c.carrier_nco_bits)) * (unsigned)c.mult_i;
+      const unsigned wk = ((unsigned)(int)codeFreq << (32 - c.code_nco_bits)) * (unsigned)c.mult_i;
+      r.w_carr_hi = (int)(wc >> 16);
+      r.w_carr_lo = (int)(wc & 0xffffu);
+      r.w_code_hi = (int)(wk >> 16);
+      r.w_code_lo = (int)(wk & 0xffffu);
+      if (carr_ok) {
+        k.cross = (long long)cross8;
+        k.dot = (long long)dot8;
+      }
+      k.freqError = (long long)f;
+      k.carrError = (long long)e;
+      k.carrNco = carrNco;
+      k.oldCarrNco = carrNco;
+      k.oldCarrError = (long long)e;
+      k.carrFreq = carrFreq;
+      k.codeError = (long long)d;
+      k.codeNco = codeNco;
+      k.oldCodeNco = codeNco;
+      k.oldCodeError = (long long)d;
+      k.codeFreq = codeFreq;
+      return;
+    }
+  }
   if (bad) {  // an estimate was off by more than one (not expected): literal forms
     at_f = dev_atan2_i32_slow(cross8, dot8);
     at_p = dev_atan2_i32_slow(py, px);
@@ -301,8 +344,6 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
     code_q = (8192 * ((int)se - (int)sl)) / (den_c > 0 ? den_c : 1);
   }
   ISR_STAMP(0)
-  const bool carr_ok = ip != 0 && qp != 0 && pip != 0 && pqp != 0;
-  const long long oce = k.oldCarrError, ode = k.oldCodeError;
   const long long ce = carr_ok ? (long long)(at_p / 2) : oce;
   const long long fe = carr_ok ? (long long)at_f : 0ll;
   if (carr_ok) {
@@ -326,7 +367,7 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
   dev_ch_carrier(r, c, k.carrFreq);
   ISR_STAMP(2)
 
-  const long long de = (ie != 0 && qe != 0 && il != 0 && ql != 0) ? (long long)code_q : ode;
+  const long long de = code_ok ? (long long)code_q : ode;
   k.codeError = de;
   {
     const long long num = (ode == (long long)(int)ode) ? (long long)(c.dll_i1 + 1) * (int)de - (long long)c.dll_i2 * (int)ode

@@ -192,13 +192,20 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
-  do {
+  // a plain test first: in the steady state the phase has completed long ago, and test_wait answers
+  // faster than try_wait (which may suspend the thread for a hardware time slice)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-  } while (!ok);
+  }
 }
 
 // The per-thread hot loop: SPT samples in groups of four.  Requires 1 <= kinc and 4*kinc < 2^32
@@ -386,7 +393,9 @@ __device__ __forceinline__ void apply_dump_counters(ChanShared &cs) {
   cs.r.r_meas[7] = g.ms_counter + (g.bit_counter << 8);
 }
 
-__device__ __forceinline__ void finalize_fast(ChanShared &cs, const StepParams &sp, const int (&A)[6], const int (&B)[6], int nsamp) {
+// End-of-block rules of the closed-form path, split in two: everything that follows from the block's
+// parameters alone (dump or not, counters, half-chip count, TIC latch, NCO phases) ...
+__device__ __forceinline__ void finalize_state(ChanShared &cs, const StepParams &sp, int nsamp) {
   gnssb200_corr &g = cs.g;
   ChRegs &r = cs.r;
   const unsigned long long n = (unsigned long long)nsamp;
@@ -396,16 +405,9 @@ __device__ __forceinline__ void finalize_fast(ChanShared &cs, const StepParams &
   const bool dumped = sp.w1 <= wtot;
   const int epoch_before = r.r_meas[7];
   if (dumped) {
-#pragma unroll
-    for (int q = 0; q < 6; q++) {
-      r.r_acc[q] = g.acc[q] + A[q];
-      g.acc[q] = B[q];
-    }
     apply_dump_counters(cs);
     g.half_chip = wtot - sp.w1;
   } else {
-#pragma unroll
-    for (int q = 0; q < 6; q++) g.acc[q] += A[q] + B[q];
     g.half_chip = sp.hc0 + wtot;
   }
   cs.dumped_last = dumped ? 1 : 0;
@@ -429,6 +431,25 @@ __device__ __forceinline__ void finalize_fast(ChanShared &cs, const StepParams &
   }
   g.carrier_phase = (uint32_t)cend;
   g.code_phase = (uint32_t)kend;
+}
+// ... and the accumulators, which need the block's sums: A = samples up to the dump (or all of them),
+// B = samples after it.  Requires cs.dumped_last from finalize_state.
+__device__ __forceinline__ void finalize_acc(ChanShared &cs, const int (&A)[6], const int (&B)[6]) {
+  gnssb200_corr &g = cs.g;
+  if (cs.dumped_last) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      cs.r.r_acc[q] = g.acc[q] + A[q];
+      g.acc[q] = B[q];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 6; q++) g.acc[q] += A[q] + B[q];
+  }
+}
+__device__ __forceinline__ void finalize_fast(ChanShared &cs, const StepParams &sp, const int (&A)[6], const int (&B)[6], int nsamp) {
+  finalize_state(cs, sp, nsamp);
+  finalize_acc(cs, A, B);
 }
 
 // literal per-sample walk of one block by a single lane (any register contents)
@@ -911,9 +932,11 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
            n_quiet ? t_quiet / n_quiet : 0, ne, t_main / ne, t_red / ne, t_isr / ne, t_sync2 / ne, t_corr / a.nblocks);
     printf("   tid %d: head(incl wait) %lld  mbar wait %lld  load %lld  load+setup %lld  post(unpack,straddle) %lld per block\n", tid, t_head / a.nblocks,
            t_wait / a.nblocks, t_load / a.nblocks, t_setup / a.nblocks, t_post / a.nblocks);
+#ifdef TRACK_PROFILE_ISR
     if (tid == 0)
       printf("   isr sections (cycles per event block): primitives %lld  pll %lld  carrier word %lld  dll %lld  code word %lld  pull-in bookkeeping %lld\n",
              g_isr_t[0] / ne, g_isr_t[1] / ne, g_isr_t[2] / ne, g_isr_t[3] / ne, g_isr_t[4] / ne, g_isr_t[5] / ne);
+#endif
     if (tid == 0)
       printf("   isr lane: finalize %lld  after_block %lld  prepare %lld per event; after_block by state after: acq %lld (%lld) conf %lld (%lld) pull %lld (%lld) track %lld (%lld)\n",
              t_fin / ne, t_after / ne, t_prep / ne, n_state[1] ? t_state[1] / n_state[1] : 0, n_state[1], n_state[2] ? t_state[2] / n_state[2] : 0, n_state[2],
@@ -1100,8 +1123,17 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
     bool event = classify_block(sp, a, a.nblocks <= 1, nx);
     publish(0, sp, event);
     uint32_t ev_phase = 0;
+#ifdef TRACK_PROFILE
+    long long c_twait = 0, c_fin = 0, c_words = 0, c_params = 0, c_rest = 0, c_ewait = 0, c_quiet = 0, n_ev = 0, n_q = 0;
+#define CP(var) { long long _c = clock64(); var += _c - _t; _t = _c; }
+#else
+#define CP(var)
+#endif
     for (long long b = 0; b < a.nblocks; b++) {
       if (sp.mode == MODE_STOP) break;
+#ifdef TRACK_PROFILE
+      long long _t = clock64();
+#endif
       const bool last = b + 1 == a.nblocks;
       const int slot = (int)(b & 1), nslot = slot ^ 1;
       if (!last) {
@@ -1113,16 +1145,30 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
           loaded = b + 1;
         }
       }
+      CP(c_ewait)
       if (!event) {  // quiet block: nothing leaves the correlator threads
         sp = nx;
         event = classify_block(sp, a, b + 2 == a.nblocks, nx);
         publish(nslot, sp, event);
+#ifdef TRACK_PROFILE
+        n_q++;
+#endif
+        CP(c_quiet)
         continue;
       }
-      int A[6] = {0, 0, 0, 0, 0, 0}, B[6] = {0, 0, 0, 0, 0, 0};
+#ifdef TRACK_PROFILE
+      n_ev++;
+#endif
+      // what follows from the block's parameters alone is settled while the correlator warps still work
+      cs.tic = sp.tic;
+      cs.g.carrier_cycle += sp.cyc_pending;
+      if (sp.mode == MODE_FAST) finalize_state(cs, sp, a.nsamp);
+      CP(c_fin)
       if (sp.mode == MODE_FAST) {
+        int A[6], B[6];
         mbar_wait(&tfull, ev_phase);
         ev_phase ^= 1;
+        CP(c_twait)
         const int4 t0 = *reinterpret_cast<const int4 *>(&totals[0]);
         const int4 t1 = *reinterpret_cast<const int4 *>(&totals[4]);
         const int4 t2 = *reinterpret_cast<const int4 *>(&totals[8]);
@@ -1132,12 +1178,8 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
         *reinterpret_cast<int4 *>(&totals[0]) = z;  // the next event block's atomics come after the publish below
         *reinterpret_cast<int4 *>(&totals[4]) = z;
         *reinterpret_cast<int4 *>(&totals[8]) = z;
-      }
-      cs.tic = sp.tic;
-      cs.g.carrier_cycle += sp.cyc_pending;
-      if (sp.mode == MODE_FAST)
-        finalize_fast(cs, sp, A, B, a.nsamp);
-      else if (sp.mode == MODE_SERIAL) {
+        finalize_acc(cs, A, B);
+      } else if (sp.mode == MODE_SERIAL) {
         mbar_wait(&dfull[slot], (uint32_t)((b >> 1) & 1));
         serial_block(cs, sp, a.code_table, fmt, a.nsamp, tiles + (size_t)slot * tile_bytes);
       } else
@@ -1151,6 +1193,7 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
         else
           isr = true;
       }
+      CP(c_words)
       const int was_mode = sp.mode;
       if (cs.halted || was_mode == MODE_IDLE)  // an idle channel has no ISR: nothing can change any more
         sp.mode = MODE_STOP;
@@ -1162,6 +1205,7 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
         event = classify_block(sp, a, b + 2 == a.nblocks, nx);
         publish(nslot, sp, event);
       }
+      CP(c_params)
       // second part, off the correlators' critical path
       if (isr) dev_gpsisr_rest(cs.k, cs.r, a.cfg, st_in);
       if (cs.dumped_last && !cs.halted && a.dumps && cs.dump_count < a.dump_cap) {
@@ -1186,7 +1230,13 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
         cs.dump_count++;
       }
       if (!last && sp.mode != MODE_STOP) apply_epoch_load(cs);  // start-of-block rule of the next block
+      CP(c_rest)
     }
+#ifdef TRACK_PROFILE
+    if (blockIdx.x == 0 && n_ev && n_q)
+      printf("control lane: %lld quiet blocks: slot wait+TMA %lld, classify+publish %lld | %lld event blocks: totals wait %lld finalize %lld isr words %lld params+publish %lld rest %lld (cycles each)\n",
+             n_q, c_ewait / (n_q + n_ev), c_quiet / n_q, n_ev, c_twait / n_ev, c_fin / n_ev, c_words / n_ev, c_params / n_ev, c_rest / n_ev);
+#endif
     // a prefetched block nobody consumed must land before the CTA may exit
     if (loaded >= 0) mbar_wait(&dfull[loaded & 1], (uint32_t)((loaded >> 1) & 1));
     rx->chan[ch] = cs.k;
@@ -1211,10 +1261,18 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
   const bool live = i0 < a.nsamp;
   const uint32_t vlut_lane = smem_u32(vlut) + 4u * (uint32_t)lane;
   int carry[6] = {0, 0, 0, 0, 0, 0};
+#ifdef TRACK_PROFILE
+  long long t_pw = 0, t_dw = 0, t_corr = 0, t_red = 0, t_all = -clock64(), nb = 0;
+#endif
   for (long long b = 0; b < a.nblocks; b++) {
     const int slot = (int)(b & 1);
     const uint32_t par = (uint32_t)((b >> 1) & 1);
+#ifdef TRACK_PROFILE
+    long long _t = clock64();
+    nb++;
+#endif
     mbar_wait(&pfull[slot], par);
+    CP(t_pw)
     const uint4 p0 = reinterpret_cast<const uint4 *>(&params[slot])[0];
     const uint4 p1 = reinterpret_cast<const uint4 *>(&params[slot])[1];
     const int2 p2 = reinterpret_cast<const int2 *>(&params[slot])[4];
@@ -1226,6 +1284,7 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
       const uint32_t hc0 = p1.x, w1 = p1.y, stale_idx = p1.z, stale_bits = p1.w;
       const uint8_t *tile = tiles + (size_t)slot * tile_bytes;
       mbar_wait(&dfull[slot], par);
+      CP(t_dw)
       int sumA[6] = {0, 0, 0, 0, 0, 0}, sumB[6] = {0, 0, 0, 0, 0, 0};
       bool anyB = false;
       {
@@ -1305,6 +1364,7 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
         }
         anyB |= !allA;
       }
+      CP(t_corr)
       if (!event) {  // no dump in this block: every chunk was pre-dump, keep the sums in registers
 #pragma unroll
         for (int q = 0; q < 6; q++) carry[q] += sumA[q];
@@ -1335,7 +1395,14 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
       if (event && mode == MODE_FAST) mbar_arrive(&tfull);
       mbar_arrive(&empty[slot]);
     }
+    CP(t_red)
   }
+#ifdef TRACK_PROFILE
+  t_all += clock64();
+  if (blockIdx.x == 0 && (tid == 0 || tid == 133) && nb)
+    printf("correlator tid %d: per block: params wait %lld  data wait %lld  load+correlate+post %lld  reduce/arrive %lld  total %lld\n", tid, t_pw / nb, t_dw / nb,
+           t_corr / nb, t_red / nb, t_all / nb);
+#endif
 }
 
 // one thread per stream: status words, TIC counter and block counter after a run
@@ -1457,6 +1524,12 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     const double m = h->cfg.clock_mult;
     const long long im = (long long)m;
     a.cfg.mult_i = ((double)im == m && im > -1024 && im < 1024) ? (int)im : 0;
+    const gnssb200_cfg &c = h->cfg;
+    auto ab = [](long long v) { return v < 0 ? -v : v; };
+    const bool pll_ok = (ab(c.pll_i1) + ab(c.pll_i2)) * (1ll << 17) + ab(c.pll_i3) * (1ll << 16) < (1ll << 31);
+    const bool dll_ok = (ab((long long)c.dll_i1 + 1) + ab(c.dll_i2)) * (1ll << 17) < (1ll << 31);
+    const int shc = 32 - c.carrier_nco_bits, shk = 32 - c.code_nco_bits;
+    a.cfg.fast32 = (a.cfg.mult_i != 0 && pll_ok && dll_ok && shc >= 0 && shc <= 8 && shk >= 0 && shk <= 8) ? 1 : 0;
   }
   const int grid = n_streams * NCH;
   static int env_spt = -1;
