@@ -36,7 +36,11 @@
 #define MODE_FAST 1
 #define MODE_SERIAL 2
 
-#define SMEM_TBL 4096  // two table rows (prn, prn+1) + 4
+// Shared-memory copy of the channel's code-table row plus the start of the next one (the reference's
+// spill-over reads).  Table indices of a closed-form block stay below hc0 + w1 (= the dump position, 2046 +
+// slew) before the dump and below the half chips one block spans (~1050) after it, each plus the few entries
+// a chunk reads ahead; larger slews take the serial path.
+#define SMEM_TBL 2304
 
 struct StepParams {
   uint32_t cph0, kph0, cinc, kinc;
@@ -343,8 +347,9 @@ __device__ __forceinline__ void apply_epoch_load(ChanShared &cs) {
   }
 }
 
-// correlator parameters of the next block from the channel's registers and correlator state
-__device__ __forceinline__ void prepare_block_params(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+// correlator parameters of the next block, part 1: what the correlator state alone decides (TIC
+// down-counter, NCO phases, half-chip count) -- independent of the channel's write registers
+__device__ __forceinline__ void prepare_block_state(ChanShared &cs, StepParams &sp, const TrackArgs &a) {
   const long long n = a.nsamp;
   if (cs.tic < n) {  // correlator.c:155-165
     sp.tic_count = (int)cs.tic;
@@ -355,17 +360,20 @@ __device__ __forceinline__ void prepare_block_params(ChanShared &cs, StepParams 
   }
   sp.tic = cs.tic;
   sp.cyc_pending = 0;
+  sp.cph0 = cs.g.carrier_phase;
+  sp.kph0 = cs.g.code_phase;
+  sp.hc0 = cs.g.half_chip & 0xffff;
+}
+// part 2: NCO increments, dump position and path selection from the write registers
+__device__ __forceinline__ void prepare_block_regs(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+  const long long n = a.nsamp;
   ChRegs &r = cs.r;
-  gnssb200_corr &g = cs.g;
   if (r.w_prn <= 0) {
     sp.mode = MODE_IDLE;
     return;
   }
   sp.cinc = (uint32_t)((r.w_carr_hi << 16) + r.w_carr_lo);
   sp.kinc = (uint32_t)((r.w_code_hi << 16) + r.w_code_lo) << 1;
-  sp.cph0 = g.carrier_phase;
-  sp.kph0 = g.code_phase;
-  sp.hc0 = g.half_chip & 0xffff;
   const long long slew_dump = (long long)r.w_slew + HALF_CHIPS;  // :172
   sp.slew_dump = (uint32_t)slew_dump;
   const long long w1 = ((long long)sp.hc0 + 1 >= slew_dump) ? 1 : slew_dump - sp.hc0;
@@ -373,9 +381,13 @@ __device__ __forceinline__ void prepare_block_params(ChanShared &cs, StepParams 
   sp.w1 = (uint32_t)w1;
   sp.stale_idx = (uint32_t)(sp.hc0 + w1);
   bool fast = (r.w_prn == tbl_prn) && r.w_prn >= 1 && r.w_prn <= 32 && slew_dump >= 1 && slew_dump < 65536 &&
-              (long long)wtot < w1 + slew_dump && (sp.hc0 + wtot + 40) < SMEM_TBL && (sp.hc0 + w1) < SMEM_TBL &&
+              (long long)wtot < w1 + slew_dump && (wtot + 40) < SMEM_TBL && (sp.hc0 + w1 + 40) < SMEM_TBL &&
               n < (1ll << 30) && sp.kinc >= 1u && sp.kinc < (1u << 30);
   sp.mode = fast ? MODE_FAST : MODE_SERIAL;
+}
+__device__ __forceinline__ void prepare_block_params(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
+  prepare_block_state(cs, sp, a);
+  prepare_block_regs(cs, sp, a, tbl_prn);
 }
 
 __device__ __forceinline__ void prepare_block(ChanShared &cs, StepParams &sp, const TrackArgs &a, int tbl_prn) {
@@ -697,7 +709,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
         nx.tic = sp.tic - (long long)n;
       }
       const unsigned long long wnext = ((unsigned long long)nx.kph0 + nk) >> 32;
-      const bool next_fast = wnext < (unsigned long long)nx.w1 + sp.slew_dump && (nx.hc0 + wnext + 40) < SMEM_TBL;
+      const bool next_fast = wnext < (unsigned long long)nx.w1 + sp.slew_dump && (wnext + 40) < SMEM_TBL;
       quiet = wtot < sp.w1 && !(sp.tic_count >= 0 && sp.tic_count < a.nsamp) && next_fast;
     }
     const uint8_t *tile = tiles + (size_t)(b & 1) * tile_bytes;
@@ -988,39 +1000,45 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// Is block `sp` an event block (reduce + control-lane work at its end)?  If not, nx = parameters of the
-// next block from the closed forms.  Same rule as the quiet test of track_loop_kernel.
-__device__ __forceinline__ bool classify_block(const StepParams &sp, const TrackArgs &a, bool last, StepParams &nx) {
+// Is block `sp` an event block (reduce + control-lane work at its end)?  Same rule as the quiet test of
+// track_loop_kernel: quiet = no dump, no TIC latch, not the last block, and the next block still fits the
+// closed-form path.
+__device__ __forceinline__ bool block_is_event(const StepParams &sp, const TrackArgs &a, bool last) {
   if (sp.mode != MODE_FAST || last) return true;
-  const unsigned long long n = (unsigned long long)a.nsamp;
-  const unsigned long long nk = n * sp.kinc, nc = n * sp.cinc;
+  const unsigned long long nk = (unsigned long long)a.nsamp * sp.kinc;
   const unsigned long long kend = (unsigned long long)sp.kph0 + nk;
-  const unsigned long long cend = (unsigned long long)sp.cph0 + nc;
   const uint32_t wtot = (uint32_t)(kend >> 32);
-  nx = sp;
-  nx.kph0 = (uint32_t)kend;
-  nx.cph0 = (uint32_t)cend;
-  nx.hc0 = sp.hc0 + wtot;
-  nx.w1 = sp.w1 - wtot;
-  nx.cyc_pending = sp.cyc_pending + (uint32_t)(cend >> 32);
-  if (sp.tic < (long long)n) {
-    nx.tic_count = (int)sp.tic;
-    nx.tic = sp.tic + a.cfg.tic_ref - (long long)n;
-  } else {
-    nx.tic_count = -1;
-    nx.tic = sp.tic - (long long)n;
-  }
-  const unsigned long long wnext = ((unsigned long long)nx.kph0 + nk) >> 32;
-  const bool next_fast = wnext < (unsigned long long)nx.w1 + sp.slew_dump && (nx.hc0 + wnext + 40) < SMEM_TBL;
+  const unsigned long long wnext = ((unsigned long long)(uint32_t)kend + nk) >> 32;
+  const bool next_fast = wnext < (unsigned long long)(sp.w1 - wtot) + sp.slew_dump && (wnext + 40) < SMEM_TBL;
   const bool quiet = wtot < sp.w1 && !(sp.tic_count >= 0 && sp.tic_count < a.nsamp) && next_fast;
   return !quiet;
 }
+// parameters of the block after a quiet block, from the closed forms
+__device__ __forceinline__ void advance_quiet(StepParams &sp, const TrackArgs &a) {
+  const unsigned long long n = (unsigned long long)a.nsamp;
+  const unsigned long long kend = (unsigned long long)sp.kph0 + n * sp.kinc;
+  const unsigned long long cend = (unsigned long long)sp.cph0 + n * sp.cinc;
+  const uint32_t wtot = (uint32_t)(kend >> 32);
+  sp.kph0 = (uint32_t)kend;
+  sp.cph0 = (uint32_t)cend;
+  sp.hc0 += wtot;
+  sp.w1 -= wtot;
+  sp.cyc_pending += (uint32_t)(cend >> 32);
+  if (sp.tic < (long long)n) {
+    sp.tic_count = (int)sp.tic;
+    sp.tic += a.cfg.tic_ref - (long long)n;
+  } else {
+    sp.tic_count = -1;
+    sp.tic -= (long long)n;
+  }
+}
 
-#define WS_CORR_THREADS 256
-#define WS_THREADS 288
-template <int MINB, int FMT>
-__global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackArgs a, const int tile_bytes) {
-  constexpr int SPT = 32;
+// SPT samples per correlator thread: 32 (256 correlator threads, shortest block latency) or 64 (128
+// threads: half the per-block overhead instructions and six resident CTAs per SM for dense grids).
+template <int MINB, int FMT, int SPT>
+__global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const TrackArgs a, const int tile_bytes) {
+  constexpr int WS_CORR_THREADS = 8192 / SPT;
+  constexpr int WS_THREADS = WS_CORR_THREADS + 32;
   constexpr int fmt = FMT;
   constexpr bool packed_native = FMT == GNSSB200_FMT_PACKED2;
   __shared__ ChanShared cs;
@@ -1119,12 +1137,11 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
       alias_tbl[slot][0] = sp.stale_bits;
       mbar_arrive(&pfull[slot]);  // release: the stores above are visible to whoever observes the phase
     };
-    StepParams nx;
-    bool event = classify_block(sp, a, a.nblocks <= 1, nx);
+    bool event = block_is_event(sp, a, a.nblocks <= 1);
     publish(0, sp, event);
     uint32_t ev_phase = 0;
 #ifdef TRACK_PROFILE
-    long long c_twait = 0, c_fin = 0, c_words = 0, c_params = 0, c_rest = 0, c_ewait = 0, c_quiet = 0, n_ev = 0, n_q = 0;
+    long long c_twait = 0, c_fin = 0, c_words = 0, c_params = 0, c_rest = 0, c_ewait = 0, c_quiet = 0, n_ev = 0, n_q = 0, c_acc = 0, c_prep = 0, c_cls = 0;
 #define CP(var) { long long _c = clock64(); var += _c - _t; _t = _c; }
 #else
 #define CP(var)
@@ -1147,8 +1164,8 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
       }
       CP(c_ewait)
       if (!event) {  // quiet block: nothing leaves the correlator threads
-        sp = nx;
-        event = classify_block(sp, a, b + 2 == a.nblocks, nx);
+        advance_quiet(sp, a);
+        event = block_is_event(sp, a, b + 2 == a.nblocks);
         publish(nslot, sp, event);
 #ifdef TRACK_PROFILE
         n_q++;
@@ -1162,9 +1179,13 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
       // what follows from the block's parameters alone is settled while the correlator warps still work
       cs.tic = sp.tic;
       cs.g.carrier_cycle += sp.cyc_pending;
-      if (sp.mode == MODE_FAST) finalize_state(cs, sp, a.nsamp);
+      const int was_mode = sp.mode;
+      if (was_mode == MODE_FAST) {
+        finalize_state(cs, sp, a.nsamp);
+        if (!last) prepare_block_state(cs, sp, a);  // sp now describes block b+1 as far as the correlator state decides it
+      }
       CP(c_fin)
-      if (sp.mode == MODE_FAST) {
+      if (was_mode == MODE_FAST) {
         int A[6], B[6];
         mbar_wait(&tfull, ev_phase);
         ev_phase ^= 1;
@@ -1179,9 +1200,11 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
         *reinterpret_cast<int4 *>(&totals[4]) = z;
         *reinterpret_cast<int4 *>(&totals[8]) = z;
         finalize_acc(cs, A, B);
-      } else if (sp.mode == MODE_SERIAL) {
+        CP(c_acc)
+      } else if (was_mode == MODE_SERIAL) {
         mbar_wait(&dfull[slot], (uint32_t)((b >> 1) & 1));
         serial_block(cs, sp, a.code_table, fmt, a.nsamp, tiles + (size_t)slot * tile_bytes);
+        if (!last) prepare_block_state(cs, sp, a);
       } else
         cs.dumped_last = 0;
       // ISR, first part: whatever can change the NCO words / slew
@@ -1194,15 +1217,16 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
           isr = true;
       }
       CP(c_words)
-      const int was_mode = sp.mode;
       if (cs.halted || was_mode == MODE_IDLE)  // an idle channel has no ISR: nothing can change any more
         sp.mode = MODE_STOP;
       else if (!last) {
-        prepare_block_params(cs, sp, a, tbl_prn);
+        prepare_block_regs(cs, sp, a, tbl_prn);
         sp.stale_bits = sp.mode == MODE_FAST ? tbl[sp.stale_idx] : 0u;
       }
+      CP(c_prep)
       if (!last) {
-        event = classify_block(sp, a, b + 2 == a.nblocks, nx);
+        event = block_is_event(sp, a, b + 2 == a.nblocks);
+        CP(c_cls)
         publish(nslot, sp, event);
       }
       CP(c_params)
@@ -1236,6 +1260,9 @@ __global__ void __launch_bounds__(WS_THREADS, MINB) track_ws_kernel(const TrackA
     if (blockIdx.x == 0 && n_ev && n_q)
       printf("control lane: %lld quiet blocks: slot wait+TMA %lld, classify+publish %lld | %lld event blocks: totals wait %lld finalize %lld isr words %lld params+publish %lld rest %lld (cycles each)\n",
              n_q, c_ewait / (n_q + n_ev), c_quiet / n_q, n_ev, c_twait / n_ev, c_fin / n_ev, c_words / n_ev, c_params / n_ev, c_rest / n_ev);
+    if (blockIdx.x == 0 && n_ev)
+      printf("   after the totals: read+accumulators %lld, isr words %lld, prepare params %lld, classify %lld, publish %lld\n", c_acc / n_ev, c_words / n_ev, c_prep / n_ev,
+             c_cls / n_ev, c_params / n_ev);
 #endif
     // a prefetched block nobody consumed must land before the CTA may exit
     if (loaded >= 0) mbar_wait(&dfull[loaded & 1], (uint32_t)((loaded >> 1) & 1));
@@ -1577,24 +1604,33 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     const char *e = getenv("GNSSB200_TRACK_WS");
     use_ws = e ? atoi(e) : 1;
   }
-  if (use_ws && hot && spt == 32) {  // warp-specialised variant: 8 correlator warps + control lane
+  if (use_ws && hot && spt == 32) {  // warp-specialised variant: correlator warps + control lane
+    constexpr int DSM_I8 = 2 * 16384 + 256, DSM_PK = 3 * 16384 + 256;
     static bool aws = false;
     if (!aws) {
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_INT8_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       aws = true;
     }
-    const bool dense_ws = force_occ ? (force_occ >= 3) : (grid > 2 * sms);
-    if (fmt == GNSSB200_FMT_INT8_IQ && dense_ws)
-      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+    // CTAs per SM the grid asks for; every CTA lives for the whole run, so a grid that does not fit in one
+    // wave pays a second, mostly empty one
+    const int per_sm = force_occ ? force_occ : (grid + sms - 1) / sms;
+    if (fmt == GNSSB200_FMT_INT8_IQ && per_sm >= 3)
+      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
-      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
-    else if (dense_ws)
-      track_ws_kernel<3, GNSSB200_FMT_PACKED2><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
+    else if (per_sm >= 5)
+      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<grid, 160, dyn, st>>>(a, tile_bytes);
+    else if (per_sm == 4)
+      track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64><<<grid, 160, dyn, st>>>(a, tile_bytes);
+    else if (per_sm == 3)
+      track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
     else
-      track_ws_kernel<2, GNSSB200_FMT_PACKED2><<<grid, WS_THREADS, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
   } else
   if (spt == 16 && use_tma && fmt == GNSSB200_FMT_PACKED2) {  // experiment: 512 threads x 16 samples
     static bool a16 = false;
