@@ -5,9 +5,11 @@
   python bench.py --impl reference --gpus N --steps K ...   the reference's own C receiver on host cores
 
 Metric (BASELINE.json): tracking channel*Msamples/s = streams x 12 channels x complex samples / time,
-closed loop (correlator + channel logic) included.  Workload: BASELINE config 5 sharded the way the
-config says -- 8 independent synthetic IF streams x 12 channels x 10 s per GPU (weak scaling; at
-N=8 this is exactly the 64-stream configuration).  One step = one pass of the whole workload.
+closed loop (correlator + channel logic) included.  Workload: BASELINE config 5 -- 64 independent
+synthetic IF streams x 12 channels x 10 s -- resident on EACH GPU (the largest single-GPU tracking
+configuration; weak scaling: N GPUs track 64*N streams, streams never leave their GPU).  The way the
+config shards itself over eight GPUs (8 streams per GPU) and config 2 (one stream) are reported beside
+it under "tracking_other_shapes".  One step = one pass of the whole workload.
 Acquisition cells/s for configs 1, 3 and 4 are measured outside the timed steps and reported under
 "acq" in the same JSON line.
 
@@ -48,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams-per-gpu", type=int, default=8)
+    ap.add_argument("--streams-per-gpu", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--fmt", default="packed2", choices=["packed2", "int8"])
     ap.add_argument("--no-acq", action="store_true")
@@ -140,6 +142,15 @@ def measured_traffic_per_sample(fmt: str):
     return d.get(f"track_dram_bytes_per_stream_sample_{fmt}")
 
 
+def profile_constant(key: str):
+    """A per-unit figure taken from a committed ncu capture (profiles/roofline_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(key)
+
+
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
     """Reference arm: the reference's own C receiver (oracle/_ref) on all host cores, one process per
@@ -181,7 +192,7 @@ def run_reference(args):
         "impl": "reference", "metric": "tracking channel*Msamples/s", "value": value, "unit": "channel*Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"C5 shard: {args.streams_per_gpu} streams x 12 ch per GPU, GPS L1 C/A closed-loop tracking",
+        "config": {"workload": f"C5: {args.streams_per_gpu} streams x 12 ch on each GPU, GPS L1 C/A closed-loop tracking",
                    "sample": f"{workers} streams x {args.ref_sample_seconds:g} s each (one process per stream)"},
         "cpu_baseline": {"value": value, "unit": "channel*Msamples/s", "cores": workers, "kind": "reference",
                          "sample": f"{workers} streams x 12 ch x {args.ref_sample_seconds:g} s, reference C receiver (gcc -O2), one process per stream"},
@@ -345,14 +356,26 @@ def run_ours(args):
     tr = measured_traffic_per_sample(args.fmt)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr * S * NS * nblk) if tr else None, "peak_source": peak_src,
-                "kernel": "track_loop_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "integer-issue bound, not HBM bound: ~20 issue slots per channel-sample x 12 channels per 0.5-2 B of input (DESIGN.md)"}
+                "kernel": "track_ws_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "instruction-issue bound, not HBM bound (DESIGN.md 4.1); the issue form of the same launch is under roofline_issue"}
+    # issue-slot form: warp-instructions the kernel executes per channel-sample (ncu smsp__inst_executed.sum of the
+    # committed capture, profiles/roofline_traffic.json) x channel-samples / launch time, against 4 issue slots per
+    # SM per clock at the SM clock sampled during the timed region
+    wi = profile_constant("track_warp_inst_per_channel_sample_" + args.fmt)
+    roofline_issue = None
+    if wi:
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        ach = wi * S * 12 * NS * nblk / (k_ms * 1e-3)
+        roofline_issue = {"bound": "issue", "achieved": ach / 1e12, "peak": 148 * 4 * sm_hz / 1e12, "unit": "T warp-inst/s",
+                          "frac": ach / (148 * 4 * sm_hz), "warp_inst_per_channel_sample": wi,
+                          "source": "ncu smsp__inst_executed.sum of the same launch shape (profiles/)"}
 
     # ---- two more tracking shapes, reported beside the headline (not part of the timed steps) ----
     also = None
     if not args.no_also:
         also = {}
-        for name, S2, secs in (("C2_single_stream_12ch_10s", 1, args.seconds), ("C5_whole_64_streams_on_one_gpu", 64, min(args.seconds, 5.0))):
+        for name, S2, secs in (("C2_single_stream_12ch_10s", 1, args.seconds), ("C5_shard_8_streams_per_gpu", 8, args.seconds),
+                               ("256_streams_on_one_gpu", 256, min(args.seconds, 2.0))):
             nb2 = int(secs * FS / NS)
             eng2 = TrackingEngine(n_streams=S2, device=local)
             scs2 = [gps_tracking_scenario(7000 + rank * 64 + s) for s in range(S2)]
@@ -446,13 +469,13 @@ def run_ours(args):
         "metric": "tracking channel*Msamples/s", "value": value, "unit": "channel*Msamples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"C5 shard: {S} streams x 12 ch x {args.seconds:g} s per GPU, GPS L1 C/A closed-loop tracking "
+        "config": {"workload": f"C5: {S} streams x 12 ch x {args.seconds:g} s on each GPU, GPS L1 C/A closed-loop tracking "
                                f"(search/confirm/pull-in/track), 8192-sample blocks",
                    "input_format": args.fmt, "l2": "inputs larger than L2 (%.0f MB per GPU per step)" % (S * stream_bytes / 1e6),
                    "streams_per_gpu": S, "blocks_per_stream": nblk,
                    "channels_tracking_at_end": sum(1 for x in states if x == 4), "channels": len(states)},
         "e2e": {"value": e2e_value, "unit": "channel*Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity_vs_reference": parity,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu, "parity_vs_reference": parity,
         "acq": acq, "tracking_other_shapes": also,
     }
     print(json.dumps(line))

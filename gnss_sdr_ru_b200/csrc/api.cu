@@ -244,7 +244,12 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
   CUDA_TRY(cudaSetDevice(h->device));
   const int S = h->n_streams;
   const size_t blk_bytes = fmt_bytes(fmt, nsamp);
-  long long chunk = (long long)((32u << 20) / (blk_bytes * (size_t)S));  // ~32 MiB per staging buffer
+  // Two staging buffers of about 1024 blocks per stream each (>= 32 MiB, <= 512 MiB): long enough that the
+  // per-launch prologue of the channel kernel (code-table row, state load / store) stays negligible.
+  size_t stage_target = blk_bytes * (size_t)S * 1024;
+  if (stage_target < ((size_t)32 << 20)) stage_target = (size_t)32 << 20;
+  if (stage_target > ((size_t)512 << 20)) stage_target = (size_t)512 << 20;
+  long long chunk = (long long)(stage_target / (blk_bytes * (size_t)S));
   if (chunk < 16) chunk = 16;
   if (chunk > nblocks) chunk = nblocks;
   const size_t dstride = (blk_bytes * (size_t)chunk + 255) & ~(size_t)255;

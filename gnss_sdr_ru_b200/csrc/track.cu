@@ -66,6 +66,10 @@ struct TrackArgs {
   int dump_cap;
   int32_t *dump_count;
   DevCfg cfg;
+  // 1, 8, 128, 2048 as run-time values: multiplying by them keeps address arithmetic of the hot loop on the
+  // FMA pipe (IMAD) instead of the ALU pipe (SHF/LOP3/IADD3), which is the busier one (ptxas would turn a
+  // multiplication by a literal power of two back into a shift)
+  uint32_t k1, k8, k128, k2048;
 };
 
 // byte k of w, sign extended, in one PRMT: selector nibble k copies the byte, nibble k|8 replicates
@@ -271,11 +275,14 @@ __device__ __forceinline__ void correlate_chunk(const uint32_t (&w)[SPT / 2], ui
 // 4-bit sample code (I,Q) and the 3-bit LO phase index a table of the finished mixer outputs
 //   vlut[phase*16 + code][lane] = I*A[phase] + Q*B[phase]   (= ival + 65536*qval, exact small integers),
 // replicated per lane so the look-up is bank-conflict free.  No unpack, no multiplies in the mixer.
+struct PipeK {
+  uint32_t k1, k8, k128, k2048;
+};
 template <int SPT>
 __device__ __forceinline__ void correlate_chunk_packed(const uint32_t (&p)[SPT / 8], uint32_t cph, uint32_t kph,
                                                        const uint32_t cinc, const uint32_t kinc, const uint32_t *tbl,
                                                        uint32_t h, uint32_t bits, const uint32_t vlut_lane /* smem byte address of vlut[0][lane] */,
-                                                       int &accE, int &accP, int &accL) {
+                                                       const PipeK K, int &accE, int &accP, int &accL) {
   int oE = sext8(bits, 0), oP = sext8(bits, 1), oL = sext8(bits, 2);
   int aE = 0, aP = 0, aL = 0;
   uint32_t hp = smem_u32(tbl + h);
@@ -283,16 +290,20 @@ __device__ __forceinline__ void correlate_chunk_packed(const uint32_t (&p)[SPT /
 #pragma unroll
   for (int g8 = 0; g8 < SPT / 8; g8++) {
     const uint32_t word = p[g8];
+    // the eight 4-bit sample codes of this word as bytes: even samples in we, odd samples in wo
+    const uint32_t we = word & 0x0F0F0F0Fu, wo = (word >> 4) & 0x0F0F0F0Fu;
     int v[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      // entry offset = (phase*16 + code) * 128 bytes: phase -> bits 13..11, code -> bits 10..7
-      const uint32_t ph = (cph >> 18) & 0x3800u;
-      const uint32_t cd = (4 * j >= 7 ? (word >> (4 * j - 7)) : (word << (7 - 4 * j))) & 0x780u;
+      // entry offset = (phase*16 + code) * 128 bytes.  One PRMT on the ALU pipe (the code byte); the LO phase
+      // (top three bits of the carrier NCO), both scalings and the NCO step are IMADs on the FMA pipe.
+      const uint32_t code = __byte_perm((j & 1) ? wo : we, 0u, 0x4440u | (uint32_t)(j >> 1));
+      const uint32_t idx = __umulhi(cph, K.k8);
+      const uint32_t addr = idx * K.k2048 + (code * K.k128 + vlut_lane);
       uint32_t t;
-      asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(vlut_lane + ph + cd));
+      asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(addr));
       v[j] = (int)t;
-      cph += cinc;
+      cph = cinc * K.k1 + cph;
     }
 #pragma unroll
     for (int g = 0; g < 2; g++) {
@@ -778,7 +789,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
         if (live && packed_native)
           correlate_chunk_packed<SPT>(pk, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc,
                                       stale_start ? alias_tbl : tbl, h, stale_start ? sp.stale_bits : tbl[hl],
-                                      smem_u32(vlut) + 4u * (uint32_t)lane, pE, pP, pL);
+                                      smem_u32(vlut) + 4u * (uint32_t)lane, PipeK{a.k1, a.k8, a.k128, a.k2048}, pE, pP, pL);
         else if (live)
           correlate_chunk<SPT>(cur, sp.cph0 + (uint32_t)i0 * sp.cinc, (uint32_t)k0, sp.cinc, sp.kinc,
                                stale_start ? alias_tbl : tbl, h, stale_start ? sp.stale_bits : tbl[hl], lut, pE, pP, pL);
@@ -1342,7 +1353,7 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
         const bool stale_start = allB && h == 0;
         if (live && packed_native)
           correlate_chunk_packed<SPT>(pk, cph0 + (uint32_t)i0 * cinc, (uint32_t)k0, cinc, kinc, stale_start ? alias_tbl[slot] : tbl, h,
-                                      stale_start ? stale_bits : tbl[hl], vlut_lane, pE, pP, pL);
+                                      stale_start ? stale_bits : tbl[hl], vlut_lane, PipeK{a.k1, a.k8, a.k128, a.k2048}, pE, pP, pL);
         else if (live)
           correlate_chunk<SPT>(cur, cph0 + (uint32_t)i0 * cinc, (uint32_t)k0, cinc, kinc, stale_start ? alias_tbl[slot] : tbl, h,
                                stale_start ? stale_bits : tbl[hl], lut, pE, pP, pL);
@@ -1546,6 +1557,10 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   a.dumps = d_dumps;
   a.dump_cap = dump_cap;
   a.dump_count = d_dump_count;
+  a.k1 = 1u;
+  a.k8 = 8u;
+  a.k128 = 128u;
+  a.k2048 = 2048u;
   static_cast<gnssb200_cfg &>(a.cfg) = h->cfg;
   {
     const double m = h->cfg.clock_mult;
