@@ -1613,13 +1613,13 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const bool dense = force_occ ? (force_occ >= 4) : (grid > 3 * sms);
-  const bool hot = use_tma && threads <= 256 && (fmt == GNSSB200_FMT_INT8_IQ || fmt == GNSSB200_FMT_PACKED2);
+  const bool hot = use_tma && nsamp <= 8192 && (fmt == GNSSB200_FMT_INT8_IQ || fmt == GNSSB200_FMT_PACKED2);
   static int use_ws = -1;
   if (use_ws < 0) {
     const char *e = getenv("GNSSB200_TRACK_WS");
     use_ws = e ? atoi(e) : 1;
   }
-  if (use_ws && hot && spt == 32) {  // warp-specialised variant: correlator warps + control lane
+  if (use_ws && hot) {  // warp-specialised variant: correlator warps + control lane
     constexpr int DSM_I8 = 2 * 16384 + 256, DSM_PK = 3 * 16384 + 256;
     static bool aws = false;
     if (!aws) {
@@ -1629,6 +1629,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<1, GNSSB200_FMT_PACKED2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       aws = true;
     }
     // CTAs per SM the grid asks for; every CTA lives for the whole run, so a grid that does not fit in one
@@ -1638,6 +1639,8 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
       track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
+    else if (env_spt == 16)
+      track_ws_kernel<1, GNSSB200_FMT_PACKED2, 16><<<grid, 544, dyn, st>>>(a, tile_bytes);
     else if (per_sm >= 5)
       track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<grid, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm == 4)
