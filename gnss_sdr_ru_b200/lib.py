@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
     L.gnssb200_synth.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, i64, vp, C.c_int, C.c_uint64, vp]
     L.gnssb200_softtrack.argtypes = [vp, P(abi.SoftTrackCfg), vp, i64, vp, C.c_int, vp, vp, vp]
     L.gnssb200_isr_math_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    for f in (L.gnssb200_find_preambles, L.gnssb200_find_time_marks):
+        f.argtypes = [vp, vp, C.c_int, i64, i64, C.c_int, C.c_int, vp, vp, vp, vp]
     L.correlator_init.argtypes = [C.c_double]
     L.Sim_GP2021_int.argtypes = [vp, C.c_long]
     if hasattr(L, "gnssb200_acq_search"):

@@ -322,6 +322,29 @@ int gnssb200_softtrack(gnssb200_handle *h, const gnssb200_softtrack_cfg *cfg, co
                        const gnssb200_softtrack_chan *chans, int n_ch, double *d_out, int32_t *d_ms_done,
                        void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (2) batched layer -- start of the navigation message in the tracking output
+ *     GPS      [firstSubFrame, activeChnList] = findPreambles(trkRslt_status, trkRslt_I_P, n)
+ *              SCI/GPS/L1/findPreambles.sci:30-169 with SCI/GPS/L1/include/navPartyChk.sci:57-99
+ *     GLONASS  [firstString, activeChnList]   = findTimeMarks(trkRslt_status, trkRslt_I_P, n)
+ *              SCI/GLONASS/L1/findTimeMarks.sci:25-66
+ * d_ip: DEVICE buffer holding the prompt in-phase value of (channel ch, code period ms) at byte offset
+ * ch*ch_stride_bytes + ms*ms_stride_bytes: a double (dtype GNSSB200_NAV_F64, e.g. field I_P of the
+ * gnssb200_softtrack output: ch_stride = ms_to_process*13*8, ms_stride = 13*8, base + 8) or an int32
+ * (GNSSB200_NAV_I32, e.g. acc[2] of the gnssb200_dump records: ch_stride = dump_cap*48, ms_stride = 48,
+ * base + 16).  active_in[ch] != 0 <=> trackResults(ch).status ~= '-' (NULL: all active).
+ * Outputs (host): first_*[ch] = the reference's 1-based millisecond index, 0 when nothing valid was found;
+ * active_out[ch] = 1 for channels that keep a valid start (may be NULL).  Synchronises cuda_stream.
+ * ------------------------------------------------------------------------------------------- */
+#define GNSSB200_NAV_F64 0
+#define GNSSB200_NAV_I32 1
+int gnssb200_find_preambles(gnssb200_handle *h, const void *d_ip, int dtype, int64_t ch_stride_bytes, int64_t ms_stride_bytes,
+                            int n_ch, int n_ms, const int32_t *active_in, int32_t *first_subframe, int32_t *active_out,
+                            void *cuda_stream);
+int gnssb200_find_time_marks(gnssb200_handle *h, const void *d_ip, int dtype, int64_t ch_stride_bytes, int64_t ms_stride_bytes,
+                             int n_ch, int n_ms, const int32_t *active_in, int32_t *first_string, int32_t *active_out,
+                             void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""Navigation-message search: the oracle against known answers on CPU, the CUDA path
+(through the C ABI) against the oracle on GPU."""
+import numpy as np
+import pytest
+
+from oracle import navbits_oracle as O
+
+
+def _gps_ip(rng, n_ms, first_ms0, amp=900.0, sigma=250.0, invert=False, integer=False):
+    """prompt values of one channel: parity-correct subframes whose first TLM bit starts at 0-based ms first_ms0"""
+    lead_sub = -(-first_ms0 // 6000)  # whole subframes before the one that starts at first_ms0
+    nsub = lead_sub + (n_ms - first_ms0) // 6000 + 2
+    bits = O.gps_nav_bits(nsub, rng)
+    p0 = 6000 * lead_sub - first_ms0
+    sig = np.repeat(2 * bits - 1, 20)[p0 : p0 + n_ms].astype(np.float64)
+    if invert:
+        sig = -sig
+    x = amp * sig + sigma * rng.standard_normal(n_ms)
+    return np.round(x).astype(np.int32) if integer else x
+
+
+def test_parity_routine_accepts_encoded_words_and_rejects_errors():
+    rng = np.random.default_rng(1)
+    bits = O.gps_nav_bits(3, rng)
+    pm = 2 * bits - 1
+    for inv in (1, -1):
+        for w in range(1, 30):
+            nd = inv * pm[30 * w - 2 : 30 * w + 30]
+            assert O.navPartyChk(nd) == -nd[1]
+            bad = nd.copy()
+            bad[5 + (w % 20)] *= -1
+            assert O.navPartyChk(bad) == 0
+    z = (2 * bits - 1)[28:60].copy()
+    z[7] = 0  # a zero "bit" (sign(0) = 0) can never pass
+    assert O.navPartyChk(z) == 0
+
+
+def test_oracle_finds_planted_subframe_and_time_mark():
+    rng = np.random.default_rng(2)
+    n_ms = 5000 + 6000 + 6000 + 1300
+    first0 = 5000 + 1234  # 0-based ms of the first preamble bit after the search offset
+    ip = np.stack([_gps_ip(rng, n_ms, first0), _gps_ip(rng, n_ms, first0 + 77, invert=True), 50.0 * rng.standard_normal(n_ms)])
+    first, act = O.findPreambles("TT-", ip)
+    assert list(first) == [first0 + 1, first0 + 77 + 1, 0] and act == [1, 2]
+    # GLONASS: time mark = the 30-bit pattern at 10 ms per bit, in transmission order (tm_bits is stored reversed)
+    tm = np.array([-1, 1, 1, -1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, -1, 1, 1, 1, -1, 1, 1, -1, -1, -1, 1, 1, 1, 1, 1])
+    n2 = 4000
+    x = np.repeat(2 * rng.integers(0, 2, size=n2 // 10) - 1, 10).astype(np.float64)
+    x[1700:2000] = np.repeat(tm[::-1], 10)
+    y = -x
+    fs, act2 = O.findTimeMarks("TT", np.stack([x * 500 + 20 * rng.standard_normal(n2), y * 400]))
+    assert list(fs) == [1701, 1701] and act2 == [1, 2]
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_gps_and_glonass():
+    from gnss_sdr_ru_b200.navbits import NavBitsEngine
+
+    rng = np.random.default_rng(3)
+    eng = NavBitsEngine()
+    try:
+        n_ms = 5000 + 2 * 6000 + 2500
+        rows, status = [], ""
+        for c in range(10):
+            first0 = 5000 + int(rng.integers(0, 5990))
+            if c == 3:
+                rows.append(60.0 * rng.standard_normal(n_ms))          # noise only: nothing found
+            elif c == 5:
+                r = _gps_ip(rng, n_ms, first0, sigma=700.0)               # noisy: false preamble hits to reject by parity
+                rows.append(r)
+            elif c == 7:
+                r = _gps_ip(rng, n_ms, first0)
+                r[first0 + 3 * 20 : first0 + 3 * 20 + 5] = 0.0            # exact zeros inside the preamble
+                rows.append(r)
+            else:
+                rows.append(_gps_ip(rng, n_ms, first0, invert=bool(c & 1)))
+            status += "-" if c == 8 else "T"
+        ip = np.stack(rows)
+        want, want_act = O.findPreambles(status, ip)
+        got, got_act = eng.findPreambles(status, ip)
+        assert np.array_equal(got, want) and got_act == want_act
+        assert (want > 0).sum() >= 6 and want[3] == 0 and want[8] == 0
+        # integer dump values (what gnssb200_track_run leaves in its dump records)
+        ipi = np.stack([_gps_ip(rng, n_ms, 5000 + 321 + 40 * c, integer=True) for c in range(4)])
+        want, want_act = O.findPreambles("TTTT", ipi)
+        got, got_act = eng.findPreambles("TTTT", ipi)
+        assert np.array_equal(got, want) and got_act == want_act and (want > 0).all()
+        # too short for the search offset / for a second preamble: nothing, no crash
+        got, got_act = eng.findPreambles("TT", ip[:2, :4000])
+        assert list(got) == [0, 0] and got_act == []
+        w2, a2 = O.findPreambles("TT", ip[:2, :9000])
+        g2, ga2 = eng.findPreambles("TT", ip[:2, :9000])
+        assert np.array_equal(g2, w2) and ga2 == a2
+        # GLONASS time marks
+        tm = np.array([-1, 1, 1, -1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, -1, 1, 1, 1, -1, 1, 1, -1, -1, -1, 1, 1, 1, 1, 1])
+        n2 = 7000
+        gl = []
+        for c in range(6):
+            x = np.repeat(2 * rng.integers(0, 2, size=n2 // 10) - 1, 10).astype(np.float64)
+            if c != 4:
+                p = int(rng.integers(0, n2 - 2300))
+                for rep in range(p, n2 - 300, 2000):
+                    x[rep : rep + 300] = np.repeat(tm[::-1], 10) * (1 if c & 1 else -1)
+            gl.append(x * 300.0 + 120.0 * rng.standard_normal(n2))
+        gl = np.stack(gl)
+        want, want_act = O.findTimeMarks("TTT-TT", gl)
+        got, got_act = eng.findTimeMarks("TTT-TT", gl)
+        assert np.array_equal(got, want) and got_act == want_act
+        assert (want > 0).sum() == 4
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_time_marks_from_device_softtrack_layout():
+    """strided device input: the I_P field of a [n_ch][ms][13] double buffer (gnssb200_softtrack output layout)"""
+    import torch
+
+    from gnss_sdr_ru_b200.navbits import NAV_F64, NavBitsEngine
+
+    rng = np.random.default_rng(4)
+    tm = np.array([-1, 1, 1, -1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, -1, 1, 1, 1, -1, 1, 1, -1, -1, -1, 1, 1, 1, 1, 1])
+    n_ch, n_ms = 3, 3000
+    out = rng.standard_normal((n_ch, n_ms, 13)) * 1000.0
+    for c in range(n_ch):
+        x = np.repeat(2 * rng.integers(0, 2, size=n_ms // 10) - 1, 10).astype(np.float64)
+        x[400 + 100 * c : 700 + 100 * c] = np.repeat(tm[::-1], 10)
+        out[c, :, 1] = 800.0 * x + 50.0 * rng.standard_normal(n_ms)
+    d = torch.from_numpy(out).cuda()
+    eng = NavBitsEngine()
+    try:
+        got, act = eng.findTimeMarks_device(d.data_ptr() + 8, NAV_F64, n_ms * 13 * 8, 13 * 8, n_ch, n_ms)
+    finally:
+        eng.close()
+    want, wact = O.findTimeMarks("TTT", out[:, :, 1])
+    assert np.array_equal(got, want) and act == wact and list(want) == [401, 501, 601]
