@@ -209,6 +209,11 @@ class SoftTrackChan(C.Structure):
     _fields_ = [("sv", C.c_int32), ("code_phase", C.c_int32), ("acquired_freq", C.c_double)]
 
 
+class IngestStat(C.Structure):
+    _fields_ = [("bytes_loaded", C.c_int64), ("bytes_output", C.c_int64), ("bytes_in_buffer", C.c_int64), ("ring_bytes", C.c_int64),
+                ("blocks_done", C.c_int64), ("finished", C.c_int32), ("overflow", C.c_int32)]
+
+
 SOFTTRACK_FIELDS = ("I_E", "I_P", "I_L", "Q_E", "Q_P", "Q_L", "carrFreq", "codeFreq", "dllDiscr", "dllDiscrFilt",
                     "pllDiscr", "pllDiscrFilt", "absoluteSample")
 

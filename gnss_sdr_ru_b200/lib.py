@@ -70,6 +70,16 @@ def lib() -> C.CDLL:
     L.gnssb200_isr_math_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     for f in (L.gnssb200_find_preambles, L.gnssb200_find_time_marks):
         f.argtypes = [vp, vp, C.c_int, i64, i64, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.gnssb200_ingest_open.argtypes = [vp, C.c_int, C.c_int, C.c_int, i64, C.c_int]
+    L.gnssb200_ingest_open.restype = vp
+    L.gnssb200_ingest_close.argtypes = [vp]
+    L.gnssb200_ingest_write.argtypes = [vp, vp, i64]
+    L.gnssb200_ingest_write.restype = i64
+    L.gnssb200_ingest_finish.argtypes = [vp]
+    L.gnssb200_ingest_pump.argtypes = [vp, i64]
+    L.gnssb200_ingest_pump.restype = i64
+    L.gnssb200_ingest_status.argtypes = [vp, P(abi.IngestStat)]
+    L.gnssb200_ingest_sync.argtypes = [vp, vp, vp]
     L.correlator_init.argtypes = [C.c_double]
     L.Sim_GP2021_int.argtypes = [vp, C.c_long]
     if hasattr(L, "gnssb200_acq_search"):

@@ -323,6 +323,38 @@ int gnssb200_softtrack(gnssb200_handle *h, const gnssb200_softtrack_cfg *cfg, co
                        void *cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * (2) batched layer -- streaming ingest: a circular buffer between a sample
+ *     producer and the GPU channel loop of ONE stream of the handle, modelled on
+ *     FE/PC_SIDE_SOFTWARE/WIN/GPS1A_SAMPLER/src/CircularBuffer.h:9-193 and the collector / writer threads of
+ *     win32_sampler.h:232-364 (the writer thread's place is taken by the tracking kernel).
+ *     One producer thread may call _write/_finish while one consumer thread calls _pump/_sync/_status.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gnssb200_ingest gnssb200_ingest;
+typedef struct gnssb200_ingest_stat {
+  int64_t bytes_loaded;     /* TotBytesLoaded */
+  int64_t bytes_output;     /* TotBytesOutput (handed to the GPU) */
+  int64_t bytes_in_buffer;  /* DataLeftInBuffer() */
+  int64_t ring_bytes;       /* CircularBufferSize */
+  int64_t blocks_done;      /* 512-us blocks tracked so far */
+  int32_t finished;         /* FinishedFillingBuffer */
+  int32_t overflow;         /* CircularBufferOverFlow */
+} gnssb200_ingest_stat;
+
+/* stream: index of the receiver (0 .. n_streams-1) this ingest feeds; ring_blocks: ring capacity in blocks of
+ * nsamp samples (the ring is pinned host memory); dump_cap: dump records kept per channel (0: none). */
+gnssb200_ingest *gnssb200_ingest_open(gnssb200_handle *h, int stream, int fmt, int nsamp, int64_t ring_blocks, int dump_cap);
+void gnssb200_ingest_close(gnssb200_ingest *g);
+/* Producer: all-or-nothing copy into the ring.  Returns bytes, or 0 after raising the overflow flag. */
+int64_t gnssb200_ingest_write(gnssb200_ingest *g, const void *data, int64_t bytes);
+void gnssb200_ingest_finish(gnssb200_ingest *g);
+/* Consumer: tracks the whole blocks available in one contiguous run (<= max_blocks if > 0).  Returns the number
+ * of blocks launched (0: none available), < 0 on error.  Asynchronous with respect to the kernels. */
+int64_t gnssb200_ingest_pump(gnssb200_ingest *g, int64_t max_blocks);
+int gnssb200_ingest_status(gnssb200_ingest *g, gnssb200_ingest_stat *out);
+/* Waits for the issued kernels; copies records [12][dump_cap] and counts [12] to the host (either may be NULL). */
+int gnssb200_ingest_sync(gnssb200_ingest *g, gnssb200_dump *h_dumps, int32_t *h_count);
+
+/* ---------------------------------------------------------------------------------------------
  * (2) batched layer -- start of the navigation message in the tracking output
  *     GPS      [firstSubFrame, activeChnList] = findPreambles(trkRslt_status, trkRslt_I_P, n)
  *              SCI/GPS/L1/findPreambles.sci:30-169 with SCI/GPS/L1/include/navPartyChk.sci:57-99
