@@ -1574,13 +1574,8 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     a.cfg.fast32 = (a.cfg.mult_i != 0 && pll_ok && dll_ok && shc >= 0 && shc <= 8 && shk >= 0 && shk <= 8) ? 1 : 0;
   }
   const int grid = n_streams * NCH;
-  static int env_spt = -1;
-  if (env_spt < 0) {
-    const char *e = getenv("GNSSB200_TRACK_SPT");
-    env_spt = e ? atoi(e) : 0;
-  }
-  const int spt = (env_spt == 16 && nsamp == 8192) ? 16 : 32;
-  int threads = (nsamp + spt - 1) / spt;
+  const int spt = 32;
+  int threads = (nsamp + spt - 1) / spt;  // track_loop_kernel: 32 samples per thread per pass
   threads = ((threads + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;
@@ -1592,27 +1587,22 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     const char *e = getenv("GNSSB200_TRACK_NO_TMA");
     no_tma = (e && atoi(e)) ? 1 : 0;
   }
-  const int use_tma = (aligned && !no_tma && nsamp <= (spt == 16 ? 512 : 256) * spt && blk_bytes <= 16384) ? 1 : 0;
+  const int use_tma = (aligned && !no_tma && nsamp <= 256 * spt && blk_bytes <= 16384) ? 1 : 0;
   const int tile_bytes = use_tma ? (int)((blk_bytes + 127) & ~(size_t)127) : 0;
   const size_t dyn = (size_t)2 * tile_bytes + ((use_tma && fmt == GNSSB200_FMT_PACKED2) ? 128 * 32 * 4 : 0);
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
     CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
-    CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 4, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
     attr_done = true;
   }
-  // few channels per SM: 128 registers buy instruction-level parallelism for the shared-memory look-ups;
-  // many channels per SM: 64 registers, four resident CTAs hide the same latencies with other channels' warps
-  static int force_occ = -1;
+  static int force_occ = -1;  // GNSSB200_TRACK_OCC: force the resident-CTAs-per-SM variant (experiments)
   if (force_occ < 0) {
     const char *e = getenv("GNSSB200_TRACK_OCC");
     force_occ = e ? atoi(e) : 0;
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  const bool dense = force_occ ? (force_occ >= 4) : (grid > 3 * sms);
   const bool hot = use_tma && nsamp <= 8192 && (fmt == GNSSB200_FMT_INT8_IQ || fmt == GNSSB200_FMT_PACKED2);
   static int use_ws = -1;
   if (use_ws < 0) {
@@ -1629,7 +1619,6 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<1, GNSSB200_FMT_PACKED2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       aws = true;
     }
     // CTAs per SM the grid asks for; every CTA lives for the whole run, so a grid that does not fit in one
@@ -1639,8 +1628,6 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
       track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
-    else if (env_spt == 16)
-      track_ws_kernel<1, GNSSB200_FMT_PACKED2, 16><<<grid, 544, dyn, st>>>(a, tile_bytes);
     else if (per_sm >= 5)
       track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<grid, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm == 4)
@@ -1650,20 +1637,8 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     else
       track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
   } else
-  if (spt == 16 && use_tma && fmt == GNSSB200_FMT_PACKED2) {  // experiment: 512 threads x 16 samples
-    static bool a16 = false;
-    if (!a16) {
-      CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
-      a16 = true;
-    }
-    track_loop_kernel<512, 1, GNSSB200_FMT_PACKED2, true, 16><<<grid, 512, dyn, st>>>(a, tile_bytes);
-  } else
-  if (hot && fmt == GNSSB200_FMT_INT8_IQ && dense)
-    track_loop_kernel<256, 4, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
-  else if (hot && fmt == GNSSB200_FMT_INT8_IQ)
+  if (hot && fmt == GNSSB200_FMT_INT8_IQ)  // GNSSB200_TRACK_WS=0: the barrier-synchronised predecessor, kept for A/B runs
     track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
-  else if (hot && dense)
-    track_loop_kernel<256, 4, GNSSB200_FMT_PACKED2, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
   else if (hot)
     track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true><<<grid, threads, dyn, st>>>(a, tile_bytes);
   else
