@@ -144,6 +144,7 @@ extern "C" void gnssb200_close(gnssb200_handle *h) {
   acq_free_workspace(h);
   cudaFree(h->d_rx);
   cudaFree(h->d_chan_flags);
+  cudaFree(h->d_sched);
   cudaFree(h->d_code_table);
   for (int i = 0; i < 2; i++) {
     cudaFree(h->stage[i]);
@@ -164,14 +165,17 @@ extern "C" int gnssb200_set_streams(gnssb200_handle *h, int n) {
   if (n == h->n_streams) return 0;
   cudaFree(h->d_rx);
   cudaFree(h->d_chan_flags);
+  cudaFree(h->d_sched);
   h->d_rx = nullptr;
   h->d_chan_flags = nullptr;
+  h->d_sched = nullptr;
   h->n_streams = 0;
   if (n > 0) {
     CUDA_TRY(cudaMalloc(&h->d_rx, sizeof(gnssb200_rx) * (size_t)n));
     CUDA_TRY(cudaMalloc(&h->d_chan_flags, sizeof(int32_t) * NCH * (size_t)n));
     CUDA_TRY(cudaMemset(h->d_rx, 0, sizeof(gnssb200_rx) * (size_t)n));
     CUDA_TRY(cudaMemset(h->d_chan_flags, 0, sizeof(int32_t) * NCH * (size_t)n));
+    CUDA_TRY(cudaMalloc(&h->d_sched, track_sched_bytes(n)));
     h->n_streams = n;
   }
   return 0;
@@ -194,6 +198,12 @@ extern "C" int gnssb200_download_rx(gnssb200_handle *h, int first, int count, gn
   if (check_range(h, first, count)) return -2;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpy(rx, h->d_rx + first, sizeof(gnssb200_rx) * (size_t)count, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks) {
+  if (!h || blocks < 0) return -1;
+  h->track_slice = blocks;
   return 0;
 }
 

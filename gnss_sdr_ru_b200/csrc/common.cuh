@@ -28,6 +28,8 @@ struct gnssb200_handle {
   int n_streams;
   gnssb200_rx *d_rx;          // [n_streams]
   int32_t *d_chan_flags;      // [n_streams*12] bit0: dumped in the last block, bit1: halted
+  long long track_slice;      // blocks per work-queue slice of the tracking kernel; 0 = automatic (gnssb200_set_track_slice)
+  void *d_sched;              // work queue of track_ws_kernel: headers / TIC counters / slots / dump counters per channel
   uint32_t *d_code_table;     // [TABLE_ENTRIES+1] packed E | P<<8 | L<<16 (int8 each), last entry 0
   cudaEvent_t ev0, ev1;
   long long launches;
@@ -49,6 +51,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
                  int nsamp, long long nblocks, int run_isr, gnssb200_dump *d_dumps, int dump_cap,
                  int32_t *d_dump_count, cudaStream_t st);
 void build_code_table_host(uint32_t *table /* TABLE_ENTRIES+1 */);
+size_t track_sched_bytes(int n_streams);
 
 // acq.cu
 void acq_free_workspace(gnssb200_handle *h);

@@ -70,6 +70,7 @@ struct TrackArgs {
   // FMA pipe (IMAD) instead of the ALU pipe (SHF/LOP3/IADD3), which is the busier one (ptxas would turn a
   // multiplication by a literal power of two back into a shift)
   uint32_t k1, k8, k128, k2048;
+  struct SchedQueue *sched;  // work queue of this launch (track_ws_kernel)
 };
 
 // byte k of w, sign extended, in one PRMT: selector nibble k copies the byte, nibble k|8 replicates
@@ -1044,6 +1045,54 @@ __device__ __forceinline__ void advance_quiet(StepParams &sp, const TrackArgs &a
   }
 }
 
+// ---- (channel, time-slice) work queue -----------------------------------------------------------------
+// A channel's blocks must run in order, but nothing ties a channel to one CTA for the whole record.  The
+// launch cuts every channel's nblocks into slices and starts one CTA per (channel, slice) item; a CTA takes
+// the next item from a FIFO ticket queue in global memory, runs the slice from the channel state in
+// gnssb200_rx (exactly what a second launch would do), stores the state and pushes (channel, slice+1).
+// The hardware block scheduler refills an SM as soon as a CTA retires, so all channels advance at the same
+// pace and every SM stays full until the end whatever the ratio of channels to SMs (a static
+// one-CTA-per-channel grid of 768 CTAs leaves 120 of the 148 SMs at 5 of 6 CTAs, and grids beyond one wave
+// leave most of the GPU idle during the last one).  Tickets are handed out in CTA start order and the item
+// behind ticket t is pushed by a CTA that holds an earlier ticket, i.e. one that is already running: no
+// waiting CTA can depend on one that has not been scheduled.
+typedef unsigned long long SchedSlot;  // low word: ticket number of the item stored here, high word: item = channel + nchan * slice
+struct SchedQueue {
+  unsigned head, tail, total, nchan;
+  long long slice_blocks;
+  long long *tic;       // [nchan] TIC down-counter of the channel at the start of its next slice
+  int32_t *dumpcnt;     // [nchan] dump records written so far (when the caller keeps no counters)
+  SchedSlot *slots;     // [nchan]
+};
+
+__global__ void sched_init_kernel(SchedQueue *q, unsigned nchan, unsigned nslices, long long slice_blocks, long long *tic,
+                                  int32_t *dumpcnt, SchedSlot *slots) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    q->head = 0;
+    q->tail = nchan;
+    q->total = nchan * nslices;
+    q->nchan = nchan;
+    q->slice_blocks = slice_blocks;
+    q->tic = tic;
+    q->dumpcnt = dumpcnt;
+    q->slots = slots;
+  }
+  if (i < nchan) {
+    slots[i] = (unsigned long long)i | ((unsigned long long)i << 32);  // ticket i = slice 0 of channel i
+    dumpcnt[i] = 0;
+    tic[i] = 0;
+  }
+}
+
+template <class T>
+__device__ __forceinline__ void copy_in_cg(T &dst, const T *src) {  // L2-coherent read of state another SM may have written
+  static_assert(sizeof(T) % 4 == 0, "word copy");
+  const int *s4 = reinterpret_cast<const int *>(src);
+  int *d4 = reinterpret_cast<int *>(&dst);
+  for (int i = 0; i < (int)(sizeof(T) / 4); i++) d4[i] = __ldcg(s4 + i);
+}
+
 // SPT samples per correlator thread: 32 (256 correlator threads, shortest block latency) or 64 (128
 // threads: half the per-block overhead instructions and six resident CTAs per SM for dense grids).
 template <int MINB, int FMT, int SPT>
@@ -1062,20 +1111,13 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   extern __shared__ __align__(128) uint8_t tiles[];
   uint32_t *vlut = reinterpret_cast<uint32_t *>(tiles + 2 * (size_t)tile_bytes);
 
-  const int s = a.first_stream + blockIdx.x / NCH, ch = blockIdx.x % NCH;
-  gnssb200_rx *rx = a.rx + s;
+  __shared__ int s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tbl_prn = rx->reg_write[ch << 3];
   const size_t blk_bytes = bytes_for(fmt, a.nsamp);
-  const uint8_t *stream_base = a.d_if + (size_t)s * a.stride;
   constexpr int CTRL = WS_CORR_THREADS;  // the control lane
-
+  SchedQueue *const q = a.sched;
+  // channel-independent tables first: they fill while the control lane may still be waiting for its item
   fill_lo_lut(lut);
-  if (tid < 12) totals[tid] = 0;
-  for (int i = tid; i < SMEM_TBL; i += WS_THREADS) {
-    long long f = (long long)tbl_prn * HALF_CHIPS + i;
-    tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
-  }
   if (packed_native) {
     const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
     const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
@@ -1086,6 +1128,29 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
       const int ival = i_lo[ph] * I + q_lo[ph] * Q, qval = q_lo[ph] * I - i_lo[ph] * Q;  // correlator.c:214-215
       vlut[i] = (uint32_t)(ival + 65536 * qval);
     }
+  }
+  if (tid == CTRL) {  // this CTA's item
+    const unsigned ticket = atomicAdd(&q->head, 1u);
+    volatile SchedSlot *slot = q->slots + ticket % q->nchan;
+    unsigned long long v;
+    while ((unsigned)(v = *slot) != ticket) __nanosleep(100);
+    __threadfence();  // acquire: the state the previous slice of this channel stored
+    s_item = (int)(v >> 32);
+  }
+  __syncthreads();
+  const int item = s_item;
+  const int chan_id = item % (int)q->nchan, slice = item / (int)q->nchan;
+  const int s = a.first_stream + chan_id / NCH, ch = chan_id % NCH;
+  gnssb200_rx *rx = a.rx + s;
+  const int tbl_prn = __ldcg(&rx->reg_write[ch << 3]);
+  const long long slice_first = (long long)slice * q->slice_blocks;          // first block of this slice within the launch
+  const long long nblocks = min(q->slice_blocks, a.nblocks - slice_first);    // blocks of this slice
+  const uint8_t *stream_base = a.d_if + (size_t)s * a.stride + (size_t)slice_first * blk_bytes;
+
+  if (tid < 12) totals[tid] = 0;
+  for (int i = tid; i < SMEM_TBL; i += WS_THREADS) {
+    long long f = (long long)tbl_prn * HALF_CHIPS + i;
+    tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   if (tid < 96) {
     const int t = tid % 48;
@@ -1098,24 +1163,25 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   long long first_block = 0;
   long long loaded = -1;  // last block whose TMA load was issued
   if (tid == CTRL) {
-    cs.k = rx->chan[ch];
-    cs.g = rx->corr[ch];
-    cs.r.w_prn = rx->reg_write[b8];
-    cs.r.w_carr_hi = rx->reg_write[b8 + 3];
-    cs.r.w_carr_lo = rx->reg_write[b8 + 4];
-    cs.r.w_code_hi = rx->reg_write[b8 + 5];
-    cs.r.w_code_lo = rx->reg_write[b8 + 6];
-    cs.r.w_epoch = rx->reg_write[b8 + 7];
-    cs.r.w_slew = rx->reg_write[b8 + 0x84];
-    for (int q = 0; q < 8; q++) cs.r.r_meas[q] = rx->reg_read[b8 + q];
-    for (int q = 0; q < 6; q++) cs.r.r_acc[q] = rx->reg_read[b8 + 0x84 + q];
-    cs.tic = rx->tic;
-    cs.dumped_last = 0;
-    cs.halted = 0;
-    cs.dump_count = a.dump_count ? a.dump_count[s * NCH + ch] : 0;
-    first_block = rx->blocks_done;
+    copy_in_cg(cs.k, &rx->chan[ch]);
+    copy_in_cg(cs.g, &rx->corr[ch]);
+    cs.r.w_prn = __ldcg(&rx->reg_write[b8]);
+    cs.r.w_carr_hi = __ldcg(&rx->reg_write[b8 + 3]);
+    cs.r.w_carr_lo = __ldcg(&rx->reg_write[b8 + 4]);
+    cs.r.w_code_hi = __ldcg(&rx->reg_write[b8 + 5]);
+    cs.r.w_code_lo = __ldcg(&rx->reg_write[b8 + 6]);
+    cs.r.w_epoch = __ldcg(&rx->reg_write[b8 + 7]);
+    cs.r.w_slew = __ldcg(&rx->reg_write[b8 + 0x84]);
+    for (int j = 0; j < 8; j++) cs.r.r_meas[j] = __ldcg(&rx->reg_read[b8 + j]);
+    for (int j = 0; j < 6; j++) cs.r.r_acc[j] = __ldcg(&rx->reg_read[b8 + 0x84 + j]);
+    const int prev_flags = slice > 0 ? __ldcg(&a.chan_flags[s * NCH + ch]) : 0;
+    cs.tic = slice > 0 ? __ldcg(&q->tic[chan_id]) : rx->tic;
+    cs.dumped_last = prev_flags & 1;
+    cs.halted = (prev_flags >> 1) & 1;
+    cs.dump_count = a.dump_count ? __ldcg(&a.dump_count[s * NCH + ch]) : (slice > 0 ? __ldcg(&q->dumpcnt[chan_id]) : 0);
+    first_block = rx->blocks_done + slice_first;
     sp.stale_bits = 0;
-    if (a.nblocks > 0 && !rx->halted) {
+    if (nblocks > 0 && !rx->halted && !cs.halted) {
       prepare_block(cs, sp, a, tbl_prn);
       if (sp.mode == MODE_FAST) sp.stale_bits = tbl[sp.stale_idx];
     } else
@@ -1148,7 +1214,7 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
       alias_tbl[slot][0] = sp.stale_bits;
       mbar_arrive(&pfull[slot]);  // release: the stores above are visible to whoever observes the phase
     };
-    bool event = block_is_event(sp, a, a.nblocks <= 1);
+    bool event = block_is_event(sp, a, nblocks <= 1);
     publish(0, sp, event);
     uint32_t ev_phase = 0;
 #ifdef TRACK_PROFILE
@@ -1157,12 +1223,12 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
 #else
 #define CP(var)
 #endif
-    for (long long b = 0; b < a.nblocks; b++) {
+    for (long long b = 0; b < nblocks; b++) {
       if (sp.mode == MODE_STOP) break;
 #ifdef TRACK_PROFILE
       long long _t = clock64();
 #endif
-      const bool last = b + 1 == a.nblocks;
+      const bool last = b + 1 == nblocks;
       const int slot = (int)(b & 1), nslot = slot ^ 1;
       if (!last) {
         // ring slot of block b+1 (parameters, alias table, tile) is free once every warp finished block b-1
@@ -1176,7 +1242,7 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
       CP(c_ewait)
       if (!event) {  // quiet block: nothing leaves the correlator threads
         advance_quiet(sp, a);
-        event = block_is_event(sp, a, b + 2 == a.nblocks);
+        event = block_is_event(sp, a, b + 2 == nblocks);
         publish(nslot, sp, event);
 #ifdef TRACK_PROFILE
         n_q++;
@@ -1236,7 +1302,7 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
       }
       CP(c_prep)
       if (!last) {
-        event = block_is_event(sp, a, b + 2 == a.nblocks);
+        event = block_is_event(sp, a, b + 2 == nblocks);
         CP(c_cls)
         publish(nslot, sp, event);
       }
@@ -1288,7 +1354,17 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
     for (int q = 1; q < 8; q++) rx->reg_read[b8 + q] = cs.r.r_meas[q];
     for (int q = 0; q < 6; q++) rx->reg_read[b8 + 0x84 + q] = cs.r.r_acc[q];
     a.chan_flags[s * NCH + ch] = (cs.dumped_last ? 1 : 0) | (cs.halted ? 2 : 0);
-    if (a.dump_count) a.dump_count[s * NCH + ch] = cs.dump_count;
+    if (a.dump_count)
+      a.dump_count[s * NCH + ch] = cs.dump_count;
+    else
+      q->dumpcnt[chan_id] = cs.dump_count;
+    q->tic[chan_id] = cs.tic;
+    const unsigned next_item = (unsigned)item + q->nchan;  // the channel's next slice
+    if (next_item < q->total) {
+      __threadfence();  // release: the state stored above, before the item becomes visible
+      const unsigned t = atomicAdd(&q->tail, 1u);
+      atomicExch(q->slots + t % q->nchan, (unsigned long long)t | ((unsigned long long)next_item << 32));
+    }
     return;
   }
   (void)first_block;
@@ -1302,7 +1378,7 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
 #ifdef TRACK_PROFILE
   long long t_pw = 0, t_dw = 0, t_corr = 0, t_red = 0, t_all = -clock64(), nb = 0;
 #endif
-  for (long long b = 0; b < a.nblocks; b++) {
+  for (long long b = 0; b < nblocks; b++) {
     const int slot = (int)(b & 1);
     const uint32_t par = (uint32_t)((b >> 1) & 1);
 #ifdef TRACK_PROFILE
@@ -1539,6 +1615,10 @@ void build_code_table_host(uint32_t *table) {
   }
 }
 
+size_t track_sched_bytes(int n_streams) {  // work-queue storage for a handle with n_streams receivers
+  return sizeof(SchedQueue) * (size_t)n_streams + (size_t)n_streams * NCH * (8 + 8 + 4) + 256;
+}
+
 int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void *d_if, size_t stride, int fmt,
                  int nsamp, long long nblocks, int run_isr, gnssb200_dump *d_dumps, int dump_cap,
                  int32_t *d_dump_count, cudaStream_t st) {
@@ -1557,6 +1637,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   a.dumps = d_dumps;
   a.dump_cap = dump_cap;
   a.dump_count = d_dump_count;
+  a.sched = nullptr;
   a.k1 = 1u;
   a.k8 = 8u;
   a.k128 = 128u;
@@ -1621,21 +1702,44 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       aws = true;
     }
-    // CTAs per SM the grid asks for; every CTA lives for the whole run, so a grid that does not fit in one
-    // wave pays a second, mostly empty one
+    // Work queue: every channel's blocks are cut into slices of slice_blocks; one CTA per (channel, slice)
+    // item, items handed out through the FIFO so that a channel's slices run in order.
+    static long long env_slice = -1;
+    if (env_slice < 0) {
+      const char *e = getenv("GNSSB200_TRACK_SLICE");
+      env_slice = e ? atoll(e) : 0;
+    }
+    // Slicing pays where the GPU is throughput bound (four or more channels per SM): there it keeps every SM
+    // full to the end.  With few channels each channel's latency is the limit, tickets land on SMs at random
+    // (two running CTAs may share an SM next to an idle one), so those runs stay one item per channel.
+    const int per_sm_need = (grid + sms - 1) / sms;
+    const long long slice_blocks = h->track_slice > 0 ? h->track_slice : (env_slice > 0 ? env_slice : (per_sm_need >= 4 ? 512 : nblocks));
+    const unsigned nslices = (unsigned)((nblocks + slice_blocks - 1) / slice_blocks);
+    const size_t n_all = (size_t)h->n_streams * NCH;
+    uint8_t *base = (uint8_t *)h->d_sched;
+    SchedQueue *qd = reinterpret_cast<SchedQueue *>(base) + first_stream;  // one header per possible first stream
+    long long *tic = reinterpret_cast<long long *>(base + sizeof(SchedQueue) * (size_t)h->n_streams) + (size_t)first_stream * NCH;
+    SchedSlot *slots = reinterpret_cast<SchedSlot *>(base + sizeof(SchedQueue) * (size_t)h->n_streams + 8 * n_all) + (size_t)first_stream * NCH;
+    int32_t *dcnt = reinterpret_cast<int32_t *>(base + sizeof(SchedQueue) * (size_t)h->n_streams + 16 * n_all) + (size_t)first_stream * NCH;
+    sched_init_kernel<<<(grid + 255) / 256, 256, 0, st>>>(qd, (unsigned)grid, nslices, slice_blocks, tic, dcnt, slots);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    a.sched = qd;
+    const unsigned items = (unsigned)grid * nslices;
+    // CTAs per SM the channels ask for -> variant (registers / samples per thread)
     const int per_sm = force_occ ? force_occ : (grid + sms - 1) / sms;
     if (fmt == GNSSB200_FMT_INT8_IQ && per_sm >= 3)
-      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
-      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (per_sm >= 5)
-      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<grid, 160, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm == 4)
-      track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64><<<grid, 160, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm == 3)
-      track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
     else
-      track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32><<<grid, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
   } else
   if (hot && fmt == GNSSB200_FMT_INT8_IQ)  // GNSSB200_TRACK_WS=0: the barrier-synchronised predecessor, kept for A/B runs
     track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);

@@ -163,6 +163,10 @@ class TrackingEngine:
             "gnssb200_track_run",
         )
 
+    def set_track_slice(self, blocks: int):
+        """blocks per work-queue slice of the tracking kernel (0 = automatic); results do not depend on it"""
+        check(self.L.gnssb200_set_track_slice(self.h, blocks), "gnssb200_set_track_slice")
+
     def launch_count(self) -> int:
         return int(self.L.gnssb200_launch_count(self.h))
 

@@ -181,6 +181,12 @@ int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stream_
                             int nsamp, int64_t nblocks, gnssb200_dump *h_dumps, int dump_cap,
                             int32_t *h_dump_count);
 
+/* Scheduling knob of the tracking kernel: the blocks of every channel are cut into slices of `blocks`
+ * blocks that are handed to CTAs through a work queue (keeps all SMs busy whatever the channel count).
+ * 0 = automatic (slices of 512 blocks from four channels per SM on, one slice per channel below).  Results do
+ * not depend on it. */
+int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks);
+
 /* Number of kernels this library has launched since open (bench.py reports it as gpu_launches). */
 int64_t gnssb200_launch_count(const gnssb200_handle *h);
 /* Device time (ms, CUDA events on the launching stream) of the most recent track/acq kernel

@@ -111,6 +111,32 @@ def test_closed_loop_multi_stream(oracle_lib, track_record):
     _compare_run(eng, orcs, recs, n)
 
 
+@pytest.mark.parametrize("slice_blocks", [1, 37, 128])
+def test_work_queue_slices_do_not_change_results(oracle_lib, track_record, slice_blocks):
+    """The (channel, slice) work queue: every channel's run cut into slices that different CTAs execute from
+    the stored channel state -- TIC latches on, false alarms, five streams, a resumed second call; all
+    records and the final state equal the oracle's single pass."""
+    rec, _ = track_record
+    n, S = 300, 5
+    over = dict(tic_period=0.0123, acq_thresh=1100)
+    recs = np.stack([np.roll(rec[: 2 * NS * n], 2 * 1013 * s) for s in range(S)])
+    eng, orcs = _setup_pair(oracle_lib, n_streams=S, cfg_over=over)
+    eng.set_track_slice(slice_blocks)
+    d1, c1 = eng.run_host(recs[:, : 2 * NS * 110], 110, NS, abi.FMT_INT8_IQ, dump_cap=700)
+    # second call continues from the device state and appends to the same record arrays
+    buf = np.ascontiguousarray(recs[:, 2 * NS * 110 :])
+    check_rc = eng.L.gnssb200_track_run_host(eng.h, buf.ctypes.data, buf.strides[0], abi.FMT_INT8_IQ, NS, n - 110, d1.ctypes.data, 700,
+                                             c1.ctypes.data)
+    assert check_rc == 0
+    eng.download()
+    for s, o in enumerate(orcs):
+        _, od, oc = o.run(recs[s], NS, n, dump_cap=700)
+        assert np.array_equal(c1[s], oc)
+        for ch in range(12):
+            assert np.array_equal(d1[s, ch, : oc[ch]], od[ch, : oc[ch]]), f"stream {s} channel {ch}"
+        assert _rx_bytes(eng.rx[s]) == _rx_bytes(o.rx)
+
+
 def test_closed_loop_tic_and_thresholds(oracle_lib, track_record):
     """TIC latches enabled (tic_period = 0.1 s), other block size, low threshold (false alarms)."""
     rec, _ = track_record
@@ -202,7 +228,9 @@ def test_closed_loop_vs_reference_golden():
     dumps, cnt = eng.run_host(g["packed"][None, :], int(g["nblk"]), int(g["nsamp"]), abi.FMT_PACKED2, dump_cap=cap)
     eng.download()
     assert np.array_equal(cnt[0], g["cnt"])
-    assert np.array_equal(dumps[0], g["dumps"].view(abi.DUMP_DTYPE).reshape(dumps[0].shape))
+    gold = g["dumps"].view(abi.DUMP_DTYPE).reshape(dumps[0].shape)
+    for ch in range(12):  # records beyond a channel's count are unspecified (device staging memory is not cleared)
+        assert np.array_equal(dumps[0, ch, : cnt[0, ch]], gold[ch, : cnt[0, ch]]), f"channel {ch}"
     assert np.array_equal(np.array(eng.rx[0].reg_read[:]), g["reg_read"])
     assert np.array_equal(np.array(eng.rx[0].reg_write[:]), g["reg_write"])
 
