@@ -18,7 +18,7 @@ Acquisition cells/s for configs 1, 3 and 4 are measured outside the timed steps 
            (gnssb200_track_run_host: pinned host record -> H2D -> kernels -> D2H of the dump records).
 `roofline`: HBM form, algorithmic bytes = 0.5 B (packed 2+2 bit) or 2 B (int8) per complex sample per
            stream, divided by the tracking kernel's launch duration; see DESIGN.md for why this path
-           is integer-issue bound long before it is HBM bound.
+           is instruction-issue bound long before it is HBM bound (`roofline_issue` is that form).
 `cpu_baseline`: the reference C receiver (oracle/_ref, compiled from the reference's own sources) on
            one host core, on stream 0 of this rank's workload copied back from the GPU; its dump
            records are also compared bit for bit with the GPU's.
