@@ -450,7 +450,7 @@ def run_ours(args):
     # ---- acquisition (configs 1, 3, 4), outside the timed steps ----
     acq = None
     if not args.no_acq:
-        acq = bench_acquisition(eng, dev, rank, world, clocks)
+        acq = bench_acquisition(eng, dev, rank, world, clocks, no_cpu=args.no_cpu)
 
     # ---- CPU baseline (rank 0): reference C receiver on stream 0, plus bit-exact check of the GPU dumps ----
     cpu = None
@@ -481,7 +481,7 @@ def run_ours(args):
     print(json.dumps(line))
 
 
-def bench_acquisition(eng, dev, rank, world, clocks):
+def bench_acquisition(eng, dev, rank, world, clocks, no_cpu=False):
     """acq cells/s for BASELINE configs 1, 3, 4 on device-resident records.  With several ranks the
     (sv, bin) grid is sharded (row r -> rank r % world) and the row tables are all-gathered (NCCL)."""
     import torch
@@ -505,6 +505,10 @@ def bench_acquisition(eng, dev, rank, world, clocks):
         ("C4_gps_10ms_x20_32prn_401bins", Settings.gps(acqSearchBand=20.0, acqCohIntegration=10, n_noncoh=20),
          gps_weak_acq_scenario(4004), 4004, dict(B=1, K=20, T=10)),
     ]
+    # bounded CPU samples (about 5-15 s each on one core): which code entries the restatement processes
+    # (config 4 is left out: one PRN of it keeps the restatement busy for minutes)
+    cpu_sample = {"C1_gps_1ms_32prn_41bins": list(range(1, 33)),
+                  "C3_glonass_5ms_14fch_121bins": list(range(-7, 7))} if not no_cpu else {}
     for name, st, sats, seed, fl in cases:
         n = ae.samples_needed(st)
         n4 = (n + 3) // 4 * 4
@@ -544,7 +548,28 @@ def bench_acquisition(eng, dev, rank, world, clocks):
         n_base = G if st.system == "glonass" else nb  # C3 counts one forward spectrum per (FCH, bin)
         flops = fl["B"] * fl["K"] * (n_base * (8 * fl["T"] * N + 5 * N * np.log2(N)) + G * (6 * N + 5 * N * np.log2(N) + 3 * N))
         tt = float(t.item())
-        out[name] = {"cells": cells, "cells_per_s": cells / tt, "ms": tt * 1e3, "kernel_ms_rank0": ae.last_kernel_ms(),
+        cpu_acq = None
+        if rank == 0 and cpu_sample.get(name):
+            # CPU side: the NumPy float64 restatement of acquisition.sci (numpy.fft = pocketfft, one
+            # thread) on a bounded sample of the same record -- a subset of the PRN / frequency-channel list --
+            # which doubles as a full-size parity check of those entries
+            from oracle import pcps_oracle
+
+            sub = cpu_sample[name]
+            host = rec.cpu().numpy().view(np.int8)[: 2 * n]
+            kw = dict(acqSearchBand=st.acqSearchBand, acqCohIntegration=st.acqCohIntegration, svList=list(sub))
+            ost = pcps_oracle.AcqSettings.glonass(**kw) if st.system == "glonass" else pcps_oracle.AcqSettings.gps(**kw)
+            t0 = time.perf_counter()
+            ora = pcps_oracle.acquisition(pcps_oracle.to_complex(host), ost)
+            dtc = time.perf_counter() - t0
+            by_sv = {int(sv): i for i, sv in enumerate(st.acqSatelliteList)}
+            same = all(int(res[by_sv[int(sv)]].bin) == o["bin"] and int(res[by_sv[int(sv)]].codePhaseRaw) == o["codePhaseRaw"]
+                       and abs(res[by_sv[int(sv)]].peakMetric - o["peakMetric"]) <= 1e-4 * o["peakMetric"] for sv, o in zip(sub, ora))
+            ccells = len(sub) * nb * N
+            cpu_acq = {"cells_per_s": ccells / dtc, "seconds": dtc, "cores": 1, "kind": "port",
+                       "sample": f"{len(sub)} of {n_sv} code entries, all {nb} bins, NumPy float64 restatement of acquisition.sci (pocketfft)",
+                       "argmax_exact_and_metric_1e-4": bool(same)}
+        out[name] = {"cells": cells, "cells_per_s": cells / tt, "ms": tt * 1e3, "kernel_ms_rank0": ae.last_kernel_ms(), "cpu_baseline": cpu_acq,
                      "algorithmic_gflop": flops / 1e9, "fp32_tflops_achieved": flops / tt / 1e12,
                      "fp32_peak_tflops": fp32_peak, "fp32_frac": flops / tt / 1e12 / fp32_peak,
                      "detected": found, "n_present": len(sats)}
