@@ -1713,7 +1713,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     // full to the end.  With few channels each channel's latency is the limit, tickets land on SMs at random
     // (two running CTAs may share an SM next to an idle one), so those runs stay one item per channel.
     const int per_sm_need = (grid + sms - 1) / sms;
-    const long long slice_blocks = h->track_slice > 0 ? h->track_slice : (env_slice > 0 ? env_slice : (per_sm_need >= 4 ? 256 : nblocks));
+    const long long slice_blocks = h->track_slice > 0 ? h->track_slice : (env_slice > 0 ? env_slice : (per_sm_need >= 4 ? 128 : nblocks));
     const unsigned nslices = (unsigned)((nblocks + slice_blocks - 1) / slice_blocks);
     const size_t n_all = (size_t)h->n_streams * NCH;
     uint8_t *base = (uint8_t *)h->d_sched;

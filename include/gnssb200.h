@@ -183,7 +183,7 @@ int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stream_
 
 /* Scheduling knob of the tracking kernel: the blocks of every channel are cut into slices of `blocks`
  * blocks that are handed to CTAs through a work queue (keeps all SMs busy whatever the channel count).
- * 0 = automatic (slices of 256 blocks -- 1 MB of packed samples, so the slices in flight stay L2 resident -- from four channels per SM on, one slice per channel below).  Results do
+ * 0 = automatic (slices of 128 blocks -- 512 KB of packed samples, so the slices in flight stay L2 resident -- from four channels per SM on, one slice per channel below).  Results do
  * not depend on it. */
 int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks);
 
