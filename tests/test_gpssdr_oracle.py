@@ -1,0 +1,89 @@
+"""GPS-SDR fixed-point acquisition, CPU side: the restatement's primitives against the
+reference's own code compiled in place, the regenerated code table against the reference's header."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import gpssdr_oracle_api as G
+
+needs_ref = pytest.mark.skipif(not os.path.isdir(G.RT), reason="reference tree not present")
+
+
+def test_code_table_hash_is_stable():
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    t = gpssdr_codes.fft_codes()
+    assert t.shape == (51, 2048, 2) and t.dtype == np.int16
+    assert int(np.hypot(t[..., 0].astype(float), t[..., 1].astype(float)).max() + 0.5) == 512  # scaled to 9 signed bits
+    assert tuple(t[0, 0]) == (11, 0) and tuple(t[0, 1]) == (-90, -89)  # first entries of prn_codes.h
+    assert gpssdr_codes.table_sha256() == "be9e4e21b1888d1861f858876b84d322b35caf822cdd708b6e67d9c1fa32fc24"
+
+
+@needs_ref
+def test_code_table_equals_reference_header():
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    txt = open(os.path.join(G.RT, "accessories", "prn_codes.h")).read()
+    body = txt[txt.index("{") + 1 : txt.index("}")]
+    ref = np.array([int(x) for x in re.split(r"[,\s]+", body.strip()) if x], dtype=np.int16)
+    assert ref.size == 208896
+    assert np.array_equal(gpssdr_codes.fft_codes().reshape(-1), ref)
+
+
+@needs_ref
+def test_primitives_match_compiled_reference():
+    L, R = G.lib(), G.ref()
+    rng = np.random.default_rng(5)
+    R1 = np.zeros(16, dtype=np.int32)
+    R2 = np.array([0, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 1, 1, 1, 1, 1], dtype=np.int32)
+    Rall = np.ones(16, dtype=np.int32)
+    for amp in (40, 900, 20000):  # small, typical, wrapping (int16 overflow must wrap identically)
+        for Rp in (R1, R2, Rall):
+            for inv in (0, 1):
+                for n in (2048, 32):
+                    x = rng.integers(-amp, amp + 1, size=(n, 2)).astype(np.int16)
+                    a, b = x.copy(), x.copy()
+                    L.gso_fft(a.ctypes.data, n, Rp.ctypes.data, inv, 1)
+                    R.gsr_fft(b.ctypes.data, n, Rp.ctypes.data, inv, 1)
+                    assert np.array_equal(a, b), (amp, inv, n)
+    for shift in (9, 10, 14):
+        A = rng.integers(-23000, 23001, size=(5000, 2)).astype(np.int16)  # products stay inside int32 (beyond that the C code overflows)
+        B = rng.integers(-23000, 23001, size=(5000, 2)).astype(np.int16)
+        c1, c2 = np.zeros_like(A), np.zeros_like(A)
+        L.gso_cmulsc(A.ctypes.data, B.ctypes.data, c1.ctypes.data, 5000, shift)
+        Ar, Br = A.copy(), B.copy()
+        R.gsr_cmulsc(Ar.ctypes.data, Br.ctypes.data, c2.ctypes.data, 5000, shift)
+        assert np.array_equal(c1, c2)
+        a2 = A.copy()
+        R.gsr_cmuls(a2.ctypes.data, Br.ctypes.data, 5000, shift)  # in-place form
+        assert np.array_equal(c1, a2)
+    for f in (-112.5, -12.5, 87.5):
+        w1, w2 = np.zeros((10, 4), np.int16), np.zeros((10, 4), np.int16)
+        L.gso_wipeoff_gen(w1.ctypes.data, f, 1000.0, 10)
+        R.gsr_wipeoff_gen(w2.ctypes.data, f, 1000.0, 10)
+        assert np.array_equal(w1, w2)
+        d = rng.integers(-3000, 3000, size=(10, 2)).astype(np.int16)
+        i1, q1, i2, q2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        L.gso_cacc(d.ctypes.data, w1.ctypes.data, 10, C.byref(i1), C.byref(q1))
+        dr = d.copy()
+        R.gsr_cacc(dr.ctypes.data, w2.ctypes.data, 10, C.byref(i2), C.byref(q2))
+        assert (i1.value, q1.value) == (i2.value, q2.value)
+    for f in (-38400.0, -38650.0, -38900.0, -39150.0):
+        s1, s2 = np.zeros((20480, 2), np.int16), np.zeros((20480, 2), np.int16)
+        L.gso_sine_gen(s1.ctypes.data, f, 2048000.0, 20480)
+        R.gsr_sine_gen(s2.ctypes.data, f, 2048000.0, 20480)
+        assert np.array_equal(s1, s2)
+    m = rng.integers(-180, 181, size=(4096, 2)).astype(np.int16)
+    m1, m2 = m.copy(), m.copy()
+    L.gso_cmag(m1.ctypes.data, 4096)
+    R.gsr_cmag(m2.ctypes.data, 4096)
+    assert np.array_equal(m1, m2)
+    p = m1.view(np.int32).reshape(-1)
+    i1, g1, i2, g2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    L.gso_max(p.ctypes.data, C.byref(i1), C.byref(g1), p.size)
+    pr = p.copy()
+    R.gsr_max(pr.ctypes.data, C.byref(i2), C.byref(g2), p.size)
+    assert (i1.value, g1.value) == (i2.value, g2.value) == (int(np.argmax(p)), int(p.max()))
