@@ -214,6 +214,11 @@ class IngestStat(C.Structure):
                 ("blocks_done", C.c_int64), ("finished", C.c_int32), ("overflow", C.c_int32)]
 
 
+class GpsSdrResult(C.Structure):
+    _fields_ = [("sv", C.c_int32), ("type", C.c_int32), ("code_phase", C.c_int32), ("doppler", C.c_int32), ("magnitude", C.c_uint32),
+                ("success", C.c_int32)]
+
+
 SOFTTRACK_FIELDS = ("I_E", "I_P", "I_L", "Q_E", "Q_P", "Q_L", "carrFreq", "codeFreq", "dllDiscr", "dllDiscrFilt",
                     "pllDiscr", "pllDiscrFilt", "absoluteSample")
 

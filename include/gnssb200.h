@@ -383,6 +383,33 @@ int gnssb200_find_time_marks(gnssb200_handle *h, const void *d_ip, int dtype, in
                              int n_ch, int n_ms, const int32_t *active_in, int32_t *first_string, int32_t *active_out,
                              void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (2) batched layer -- GPS-SDR fixed-point FFT acquisition, bit exact with the
+ *     reference's portable arithmetic (RT = trunk/GNSS_SOFTWARE_RECEIVERS/REALTIME_RECEIVERS/GPS/
+ *     GPS_SDR_REAL_TIME_GPS_RECEIVER):
+ *       Acq_Command_S Acquisition::doAcqStrong(int32 sv, int32 doppmin, int32 doppmax)  RT/objects/acquisition.cpp:244
+ *       Acq_Command_S Acquisition::doAcqWeak  (int32 sv, int32 doppmin, int32 doppmax)  RT/objects/acquisition.cpp:433
+ *     each preceded by Acquisition::doPrepIF(type, buff) (:182), for a list of satellites in one call.
+ * iq         host buffer of complex int16 (i, q) at 2.048 Msps as doPrepIF receives it: 1 ms (type 0, strong)
+ *            or 310 ms (type 2, weak)
+ * fif        intermediate frequency the wipe-off tables are built for (IF_FREQUENCY 38400, signaldef.h:34)
+ * prn_codes  the pre-FFT'd code table PRN_Codes (RT/accessories/prn_codes.h): [n_codes][2048] complex int16;
+ *            gnss_sdr_ru_b200/gpssdr_codes.py regenerates it
+ * sv_list    0-based rows of that table (the reference's _sv), n_sv of them
+ * doppmin, doppmax  Hz, searched kHz bins lcv = doppmin/1000 .. doppmax/1000 - 1 (within +-100 kHz)
+ * results[i] the fields doAcq* fills in Acq_Command_S (RT/includes/structs.h:130-162)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gnssb200_gpssdr_result {
+  int32_t sv;
+  int32_t type;        /* ACQ_TYPE_STRONG 0 / ACQ_TYPE_WEAK 2 */
+  int32_t code_phase;  /* samples at 2.048 Msps */
+  int32_t doppler;     /* Hz */
+  uint32_t magnitude;
+  int32_t success;     /* magnitude > THRESH_* (both 0 in the reference, config.h:72,74) */
+} gnssb200_gpssdr_result;
+int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, int type, double fif, const int16_t *prn_codes, int n_codes,
+                            const int32_t *sv_list, int n_sv, int doppmin, int doppmax, gnssb200_gpssdr_result *results);
+
 #ifdef __cplusplus
 }
 #endif

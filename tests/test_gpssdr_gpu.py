@@ -1,0 +1,69 @@
+"""GPS-SDR fixed-point acquisition on the GPU against the restatement (oracle/gpssdr_oracle.c, pinned against
+the reference's compiled primitives): magnitude, code phase and Doppler bit exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FS, FIF = 2048000.0, 38400.0
+
+
+def _record(rng, ms, sats, sigma=8.0):  # AGC_BITS 6 (RT/includes/config.h:101): samples within about +-32
+    """complex int16 at 2.048 Msps: sum of C/A signals (sv 0-based, amplitude, doppler Hz, code offset samples) + noise"""
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    chips = gpssdr_codes.prn_gen()
+    n = ms * 2048
+    t = np.arange(n) / FS
+    x = sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    for sv, amp, dopp, off in sats:
+        chip_idx = (np.floor((np.arange(n) + off) * 1023.0 / 2048.0)).astype(np.int64) % 1023
+        data = np.where((np.arange(n) // (20 * 2048) + sv) % 3 == 0, -1.0, 1.0)  # some 20-ms data bits
+        x += amp * chips[chip_idx, sv] * data * np.exp(2j * np.pi * (FIF + dopp) * t + 1j * 0.3 * sv)
+    out = np.empty((n, 2), dtype=np.int16)
+    out[:, 0] = np.round(x.real)
+    out[:, 1] = np.round(x.imag)
+    return out
+
+
+def test_weak_and_strong_match_oracle():
+    from gnss_sdr_ru_b200 import gpssdr_codes
+    from gnss_sdr_ru_b200.gpssdr_acq import Acquisition
+    from oracle import gpssdr_oracle_api as G
+
+    rng = np.random.default_rng(12)
+    codes = gpssdr_codes.fft_codes()
+    acq = Acquisition(fif=FIF)
+    try:
+        # ---- weak: 310 ms, three satellites present (one weak), two absent ----
+        rec = _record(rng, 310, [(3, 1.2, 1730.0, 517), (17, 0.6, -2210.0, 1201), (30, 0.3, 480.0, 77)])
+        svs = [3, 17, 30, 8, 24]
+        got = acq.doAcqWeak(rec, svs, -3000, 3000)
+        o = G.GpsSdrAcquisition(fif=FIF)
+        o.doPrepIF(2, rec)
+        for sv, g in zip(svs, got):
+            w = o.doAcqWeak(codes[sv], -3000, 3000)
+            assert (g["code_phase"], g["doppler"], g["magnitude"]) == (w["code_phase"], w["doppler"], w["magnitude"]), (sv, g, w)
+        # the two stronger ones are where they were put: the reported Doppler is lcv*1000 + lcv2*250 + r*25 while DFT row r
+        # sits at r*25 - 112.5 Hz (acquisition.cpp:108,551), hence the 112.5 Hz offset
+        assert abs(got[0]["doppler"] - 112.5 - 1730) <= 100 and abs(got[1]["doppler"] - 112.5 + 2210) <= 100
+        assert got[0]["magnitude"] > 5 * got[3]["magnitude"] and got[1]["magnitude"] > 3 * got[4]["magnitude"]
+        # ---- strong: 1 ms ----
+        rec1 = _record(rng, 1, [(5, 4.0, 2400.0, 300), (11, 3.0, -3600.0, 1999)])
+        svs1 = [5, 11, 2]
+        got1 = acq.doAcqStrong(rec1, svs1, -5000, 5000)
+        o.doPrepIF(0, rec1)
+        for sv, g in zip(svs1, got1):
+            w = o.doAcqStrong(codes[sv], -5000, 5000)
+            assert (g["code_phase"], g["doppler"], g["magnitude"]) == (w["code_phase"], w["doppler"], w["magnitude"]), (sv, g, w)
+        assert got1[0]["code_phase"] == 300 and got1[1]["code_phase"] == 1999
+        # ---- large amplitudes: int16 wrap-around inside the unscaled forward FFT must wrap identically ----
+        rec2 = _record(rng, 1, [(7, 900.0, 1000.0, 100)], sigma=700.0)
+        got2 = acq.doAcqStrong(rec2, [7, 9], -2000, 2000)
+        o.doPrepIF(0, rec2)
+        for sv, g in zip([7, 9], got2):
+            w = o.doAcqStrong(codes[sv], -2000, 2000)
+            assert (g["code_phase"], g["doppler"], g["magnitude"]) == (w["code_phase"], w["doppler"], w["magnitude"]), (sv, g, w)
+        o.close()
+    finally:
+        acq.close()
