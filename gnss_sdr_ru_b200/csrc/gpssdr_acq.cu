@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int NS = 2048, ROWLEN = NS + 201, NT = 512;
+constexpr int NS = 2048, ROWLEN = NS + 201, NT = 1024, SCR = NS + NS / 32;  // SCR: padded scratch of fft2048
 
 struct Cpx16 {
   int16_t i, q;
@@ -49,13 +49,18 @@ __device__ __forceinline__ uint32_t cmul_shift(uint32_t a, uint32_t b, int shift
 }
 
 // In-place 2048-point FFT of the reference (fft.cpp): bit-reversal shuffle, then 11 ranks of 1024 butterflies
-// (bfly / bfly_noscale :401-440).  x: 2048 packed CPX in shared memory, scratch: 2048 words, tw: the 1024
+// (bfly / bfly_noscale :401-440).  x: 2048 packed CPX in shared memory, scratch: SCR words, tw: the 1024
 // twiddles (i, q) of W or iW.  rflags bit r = scale rank r by >>1 first.  All threads of the CTA.
 __device__ void fft2048(uint32_t *x, uint32_t *scratch, const uint32_t *__restrict__ tw, unsigned rflags) {
   const int tid = threadIdx.x;
-  for (int l = tid; l < NS; l += NT) scratch[l] = x[l];
+  // doShuffle :298-310 (11-bit reversal).  The copy is padded by one word per 32: the bit-reversed read of 32
+  // consecutive l differs only in the high address bits, which would put the whole warp on one bank.
+  for (int l = tid; l < NS; l += NT) scratch[l + (l >> 5)] = x[l];
   __syncthreads();
-  for (int l = tid; l < NS; l += NT) x[l] = scratch[__brev((unsigned)l) >> 21];  // doShuffle :298-310 (11-bit reversal)
+  for (int l = tid; l < NS; l += NT) {
+    const int src = (int)(__brev((unsigned)l) >> 21);
+    x[l] = scratch[src + (src >> 5)];
+  }
   __syncthreads();
   for (int r = 0; r < 11; r++) {
     const int bsize = 1 << r, nblocks = 1024 >> r;
@@ -82,7 +87,7 @@ __device__ void fft2048(uint32_t *x, uint32_t *scratch, const uint32_t *__restri
 // doPrepIF: one CTA per (offset, millisecond) row
 __global__ void __launch_bounds__(NT) gsa_prep_kernel(const uint32_t *iq, int ms, const uint32_t *wipe /* [4][10*2048] */,
                                                       const uint32_t *twf, uint32_t *rows /* [4*ms][ROWLEN] */) {
-  __shared__ uint32_t x[NS], scratch[NS];
+  __shared__ uint32_t x[NS], scratch[SCR];
   const int row = blockIdx.x, off = row / ms, m = row % ms, tid = threadIdx.x;
   for (int j = tid; j < NS; j += NT)
     x[j] = cmul_shift(iq[(size_t)m * NS + j], wipe[(size_t)off * 10 * NS + (m % 10) * NS + j], 14);
@@ -118,7 +123,7 @@ __device__ Best block_first_max(int mag, int idx, Best *red) {
 // doAcqStrong: one CTA per (sv, kHz bin, 250 Hz offset)
 __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, const uint32_t *codes, const int *sv_list, int nd, int l0,
                                                         const uint32_t *twi, unsigned rflags, Best *out) {
-  __shared__ uint32_t x[NS], scratch[NS];
+  __shared__ uint32_t x[NS], scratch[SCR];
   __shared__ Best red[NT / 32];
   const int combo = blockIdx.x % (nd * 4), svi = blockIdx.x / (nd * 4);
   const int l = l0 + combo / 4, l2 = combo % 4, tid = threadIdx.x;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, cons
   extern __shared__ uint32_t sm[];
   uint32_t *coh = sm;                       // [10][2048] packed CPX
   int *power = (int *)(sm + 10 * NS);       // [10][2048]
-  uint32_t *scratch = sm + 20 * NS;         // [2048]
+  uint32_t *scratch = sm + 20 * NS;         // [SCR]
   __shared__ Best red[NT / 32];
   __shared__ int4 dsh[100];                 // dft_rows[r][j]: i, nq, q, ni
   const int per_sv = nd * 8, combo = blockIdx.x % per_sv, svi = blockIdx.x / per_sv;
@@ -299,7 +304,7 @@ extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, in
     if (type == 0)
       gsa_strong_kernel<<<n_out, NT>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_out);
     else {
-      const size_t smem = (size_t)21 * NS * 4;
+      const size_t smem = ((size_t)20 * NS + SCR) * 4;
       e = cudaFuncSetAttribute(gsa_weak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e == cudaSuccess) gsa_weak_kernel<<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_dft, d_out);
     }
