@@ -141,6 +141,8 @@ class SynthSat(C.Structure):
         ("data_seed", C.c_int32),
         ("pad_", C.c_int32),
         ("data_rate_hz", C.c_double),
+        ("data_bits", C.c_void_p),
+        ("n_data_bits", C.c_int64),
     ]
 
 

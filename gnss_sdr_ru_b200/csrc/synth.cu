@@ -20,6 +20,7 @@ struct SynthSat {
   int32_t table_row;             // row in the chip table
   uint32_t data_seed;            // 0: no data
   uint32_t samples_per_bit;
+  uint32_t bits_off, n_bits;     // explicit data bits: n_bits entries of the bit pool starting at bits_off (n_bits = 0: none)
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
@@ -31,7 +32,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
 
 // chips: int8 [rows][1024]
 __global__ void synth_kernel(uint8_t *out, size_t stride, int fmt, int64_t n_samples, const SynthSat *sats, int n_sats,
-                             const int8_t *chips, uint64_t seed) {
+                             const int8_t *chips, uint64_t seed, const uint8_t *bit_pool) {
   const int s = blockIdx.y;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // 4 complex samples per thread
   if (i0 >= n_samples) return;
@@ -47,7 +48,10 @@ __global__ void synth_kernel(uint8_t *out, size_t stride, int fmt, int64_t n_sam
     for (int e = 0; e < 4; e++) {
       const int chip = chips[st.table_row * 1024 + (int)(cp >> 32)];
       float a = st.amp * (float)chip;
-      if (st.data_seed) {
+      if (st.n_bits) {
+        const uint64_t bit = (uint64_t)(i0 + e) / st.samples_per_bit;
+        if (bit_pool[st.bits_off + (uint32_t)(bit % st.n_bits)]) a = -a;
+      } else if (st.data_seed) {
         const uint64_t bit = (uint64_t)(i0 + e) / st.samples_per_bit;
         if (mix64(bit * 0x9E3779B97F4A7C15ULL + st.data_seed) & 1) a = -a;
       }
@@ -121,6 +125,7 @@ extern "C" int gnssb200_synth(gnssb200_handle *h, void *d_out, size_t stride, in
     chips_dev = h->device;
   }
   std::vector<SynthSat> hs((size_t)n_streams * n_sats);
+  std::vector<uint8_t> pool;  // explicit data bits of all emitters, back to back
   for (size_t i = 0; i < hs.size(); i++) {
     const gnssb200_synth_sat &g = sats[i];
     SynthSat &d = hs[i];
@@ -138,15 +143,27 @@ extern "C" int gnssb200_synth(gnssb200_handle *h, void *d_out, size_t stride, in
     d.code_ph0 = (uint64_t)(fmod(g.code_phase_chips, (double)d.code_len) * 4294967296.0);
     d.data_seed = (uint32_t)g.data_seed;
     d.samples_per_bit = (uint32_t)(g.samp_rate / (g.data_rate_hz > 0 ? g.data_rate_hz : 50.0));
+    d.bits_off = d.n_bits = 0;
+    if (g.data_bits && g.n_data_bits > 0) {
+      d.bits_off = (uint32_t)pool.size();
+      d.n_bits = (uint32_t)g.n_data_bits;
+      pool.insert(pool.end(), g.data_bits, g.data_bits + g.n_data_bits);
+    }
+  }
+  uint8_t *d_pool = nullptr;
+  if (!pool.empty()) {
+    CUDA_TRY(cudaMalloc(&d_pool, pool.size()));
+    CUDA_TRY(cudaMemcpyAsync(d_pool, pool.data(), pool.size(), cudaMemcpyHostToDevice, st));
   }
   SynthSat *d_sats = nullptr;
   CUDA_TRY(cudaMalloc(&d_sats, hs.size() * sizeof(SynthSat)));
   CUDA_TRY(cudaMemcpyAsync(d_sats, hs.data(), hs.size() * sizeof(SynthSat), cudaMemcpyHostToDevice, st));
   const int threads = 256;
   dim3 grid((unsigned)((n_samples / 4 + threads - 1) / threads), (unsigned)n_streams);
-  synth_kernel<<<grid, threads, 0, st>>>((uint8_t *)d_out, stride, fmt, n_samples, d_sats, n_sats, d_chips, seed);
+  synth_kernel<<<grid, threads, 0, st>>>((uint8_t *)d_out, stride, fmt, n_samples, d_sats, n_sats, d_chips, seed, d_pool);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(st));  // hs / d_sats lifetimes
   cudaFree(d_sats);
+  cudaFree(d_pool);
   return 0;
 }

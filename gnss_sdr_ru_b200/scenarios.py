@@ -48,6 +48,7 @@ def synth_sat_array(scenarios: list) -> tuple:
     """ctypes array of gnssb200_synth_sat [n_streams*12] for the device generator."""
     n_sats = max(len(sc.sats) for sc in scenarios)
     arr = (abi.SynthSat * (len(scenarios) * n_sats))()
+    keep = []
     for s, sc in enumerate(scenarios):
         for k in range(n_sats):
             d = arr[s * n_sats + k]
@@ -66,6 +67,12 @@ def synth_sat_array(scenarios: list) -> tuple:
             d.carrier_phase_cycles = sat.carrier_phase_cycles
             d.data_seed = sat.data_seed or 0
             d.data_rate_hz = sat.data_rate_hz
+            if sat.data_bits is not None:
+                bits = np.ascontiguousarray(sat.data_bits, dtype=np.uint8)
+                keep.append(bits)  # the array must outlive the ctypes pointer
+                d.data_bits = bits.ctypes.data
+                d.n_data_bits = bits.size
+    arr._keepalive = keep
     return arr, n_sats
 
 

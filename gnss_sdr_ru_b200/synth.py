@@ -46,6 +46,7 @@ class Sat:
     carrier_phase_cycles: float = 0.0
     data_seed: int | None = None  # None -> no data modulation
     data_rate_hz: float = 50.0  # GPS 50 bps; GLONASS L1OF 100 sym/s (meander)
+    data_bits: np.ndarray = field(default=None, repr=False, compare=False)  # explicit bits (0/1), repeated cyclically (device generator)
     _chips: np.ndarray = field(default=None, repr=False, compare=False)
 
     def carrier_if(self) -> float:
@@ -84,7 +85,11 @@ def make_record(
     out = np.empty(2 * n_samples, dtype=np.int8)
     data_bits = {}
     for k, s in enumerate(sats):
-        if s.data_seed is not None:
+        if s.data_bits is not None:  # explicit bits, cyclic; bit 1 inverts the carrier (as the device generator)
+            nbits = int(n_samples / fs * s.data_rate_hz) + 2
+            b = np.asarray(s.data_bits, dtype=np.int64)
+            data_bits[k] = (1 - 2 * b[np.arange(nbits) % b.size]).astype(np.float64)
+        elif s.data_seed is not None:
             nbits = int(n_samples / fs * s.data_rate_hz) + 2
             data_bits[k] = (2 * np.random.default_rng(s.data_seed).integers(0, 2, nbits) - 1).astype(np.float64)
     sigma = np.sqrt(0.5)  # per component, complex noise power 1

@@ -218,9 +218,11 @@ typedef struct gnssb200_synth_sat {
   double code_hz;           /* chipping rate including code Doppler */
   double code_phase_chips;  /* code phase of sample 0 */
   double carrier_phase_cycles;
-  int32_t data_seed;        /* 0: no data modulation */
+  int32_t data_seed;        /* 0: no data modulation (unless data_bits is given) */
   int32_t pad_;
   double data_rate_hz;      /* 50 (GPS) / 100 (GLONASS meander) */
+  const uint8_t *data_bits; /* optional HOST array of explicit data bits (0/1), repeated cyclically; NULL: pseudo-random bits from data_seed */
+  int64_t n_data_bits;
 } gnssb200_synth_sat;
 
 /* sats: [n_streams * n_sats].  fmt INT8_IQ or PACKED2; n_samples multiple of 4.  Synchronous. */

@@ -134,3 +134,64 @@ def test_time_marks_from_device_softtrack_layout():
         eng.close()
     want, wact = O.findTimeMarks("TTT", out[:, :, 1])
     assert np.array_equal(got, want) and act == wact and list(want) == [401, 501, 601]
+
+
+@pytest.mark.gpu
+def test_chain_integer_tracking_to_preambles_on_device():
+    """The whole integer-receiver chain without leaving the device: a 19 s GPS record carrying parity-correct
+    subframes (generated on the GPU), closed-loop tracking (search -> confirm -> pull-in -> tracking), then
+    findPreambles reading the prompt values straight from the device dump records (int32 acc[2], 48-byte
+    stride).  The result must equal the oracle's on the downloaded records, and the subframe period must be
+    visible in them."""
+    import ctypes as C
+
+    import torch
+
+    from gnss_sdr_ru_b200 import abi
+    from gnss_sdr_ru_b200.lib import check, lib
+    from gnss_sdr_ru_b200.navbits import NAV_I32, NavBitsEngine
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+    from gnss_sdr_ru_b200.scenarios import TrackScenario, synth_sat_array
+    from gnss_sdr_ru_b200.synth import Sat
+
+    rng = np.random.default_rng(21)
+    NSB, nblk = 8192, 37110  # 19.0 s
+    sats, prns = [], [0] * 12
+    for i, (prn, dop) in enumerate(((5, 1210.0), (12, -2890.0), (23, 2240.0), (30, -760.0))):
+        bits = O.gps_nav_bits(4, rng).astype(np.uint8)  # 4 subframes, repeated cyclically
+        sats.append(Sat(prn=prn, doppler_hz=dop, cn0_dbhz=50.0, code_phase_chips=100.0 + 211.0 * i, data_bits=bits))
+        prns[2 * i] = prn
+    eng = TrackingEngine(n_streams=1)
+    eng.simple_cold_allocate(0, prns)
+    for i, s in enumerate(sats):  # start each channel in the Doppler bin of its satellite
+        eng.warm_start(0, 2 * i, int(round(s.doppler_hz / 1000.0)))
+    eng.upload()
+    L = lib()
+    n = NSB * nblk
+    d_if = torch.empty(n // 2, dtype=torch.uint8, device="cuda")
+    arr, nsat = synth_sat_array([TrackScenario(sats=sats, prns=[], n_freq=[])])
+    check(L.gnssb200_synth(eng.h, d_if.data_ptr(), n // 2, abi.FMT_PACKED2, 1, n, C.addressof(arr), nsat, 4242, None), "synth")
+    cap = 19200
+    d_dumps = torch.zeros((12, cap, 48), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(12, dtype=torch.int32, device="cuda")
+    eng.run_device(d_if.data_ptr(), n // 2, nblk, NSB, abi.FMT_PACKED2, d_dumps_ptr=d_dumps.data_ptr(), dump_cap=cap, d_count_ptr=d_cnt.data_ptr())
+    torch.cuda.synchronize()
+    eng.download()
+    cnt = d_cnt.cpu().numpy()
+    states = [int(eng.rx[0].chan[ch].state) for ch in range(12)]
+    assert [states[2 * i] for i in range(4)] == [4, 4, 4, 4], states  # all four in CHANNEL_TRACKING
+    n_ms = int(cnt[[0, 2, 4, 6]].min())
+    assert n_ms > 18500
+    nav = NavBitsEngine(handle=eng.h)
+    status = "".join("T" if (ch % 2 == 0 and ch < 8) else "-" for ch in range(12))
+    first, act = nav.findPreambles_device(d_dumps.data_ptr() + 16, NAV_I32, cap * 48, 48, 12, n_ms, status)
+    recs = d_dumps.cpu().numpy().view(abi.DUMP_DTYPE).reshape(12, cap)
+    ip = recs["acc"][:, :n_ms, 2].astype(np.int32)
+    want, wact = O.findPreambles(status, ip)
+    assert np.array_equal(first, want) and act == wact
+    assert act == [1, 3, 5, 7], (first, act)
+    for ch in (0, 2, 4, 6):  # a second preamble one subframe later, where the reference looks for it
+        sgn = np.sign(ip[ch])
+        pat = np.repeat(np.array([1, -1, -1, -1, 1, -1, 1, 1]), 20)
+        k0 = int(first[ch]) - 1
+        assert abs(int(np.dot(sgn[k0 + 6000 : k0 + 6160], pat))) > 153
