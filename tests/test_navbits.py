@@ -195,3 +195,57 @@ def test_chain_integer_tracking_to_preambles_on_device():
         pat = np.repeat(np.array([1, -1, -1, -1, 1, -1, 1, 1]), 20)
         k0 = int(first[ch]) - 1
         assert abs(int(np.dot(sgn[k0 + 6000 : k0 + 6160], pat))) > 153
+
+
+@pytest.mark.gpu
+def test_chain_glonass_acquisition_tracking_time_marks_on_device():
+    """The GLONASS Scilab chain on the GPU: record synthesised on the device (three frequency channels, 100 sym/s
+    strings that end in the 30-symbol time mark), acquisition -> preRun -> floating-point tracking with the
+    results left in HBM -> findTimeMarks reading the I_P field of that buffer.  Indices equal the oracle's on the
+    downloaded buffer, and consecutive marks are one string (2000 ms) apart."""
+    import ctypes as C
+
+    import torch
+
+    from gnss_sdr_ru_b200 import abi
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.lib import check, lib
+    from gnss_sdr_ru_b200.navbits import NAV_F64, NavBitsEngine
+    from gnss_sdr_ru_b200.scenarios import TrackScenario, synth_sat_array
+    from gnss_sdr_ru_b200.softtrack import SoftTrackingEngine, TrackSettings, preRun
+    from gnss_sdr_ru_b200.synth import Sat
+
+    rng = np.random.default_rng(33)
+    tm = np.array([-1, 1, 1, -1, 1, -1, -1, 1, -1, -1, -1, -1, 1, -1, 1, -1, 1, 1, 1, -1, 1, 1, -1, -1, -1, 1, 1, 1, 1, 1])
+    ms = 4300
+    sats = []
+    for i, (k, dop) in enumerate(((-4, 1810.0), (1, -2440.0), (5, 630.0))):
+        string = np.concatenate([2 * rng.integers(0, 2, size=170) - 1, tm[::-1]])  # 1.7 s of symbols + 0.3 s time mark
+        bits = ((1 - np.tile(string, 3)) // 2).astype(np.uint8)
+        sats.append(Sat(system="glonass", prn=k, cn0_dbhz=49.0, doppler_hz=dop, code_phase_chips=60.0 + 133.0 * i, data_bits=bits, data_rate_hz=100.0))
+    L = lib()
+    acq_eng = AcquisitionEngine()
+    n = 16000 * (ms + 20)
+    d_rec = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    arr, nsat = synth_sat_array([TrackScenario(sats=sats, prns=[], n_freq=[])])
+    check(L.gnssb200_synth(acq_eng.h, d_rec.data_ptr(), 2 * n, abi.FMT_INT8_IQ, 1, n, C.addressof(arr), nsat, 909, None), "synth")
+    head = d_rec[: 2 * 16000 * 11].cpu().numpy().view(np.int8)
+    acq = acq_eng.acquisition(head, Settings.glonass(acqSatelliteList=[-4, 0, 1, 5]))
+    ts = TrackSettings(msToProcess=ms)
+    channel = preRun(acq, ts)
+    assert sorted(c["FCH"] for c in channel) == [-4, 1, 5]
+    n_ch = len(channel)
+    d_out = torch.zeros((n_ch, ms, 13), dtype=torch.float64, device="cuda")
+    d_done = torch.zeros(n_ch, dtype=torch.int32, device="cuda")
+    SoftTrackingEngine(handle=acq_eng.h).tracking_device(d_rec.data_ptr(), n, channel, ts, d_out.data_ptr(), d_done.data_ptr())
+    assert d_done.cpu().tolist() == [ms] * n_ch
+    nav = NavBitsEngine(handle=acq_eng.h)
+    first, act = nav.findTimeMarks_device(d_out.data_ptr() + 8, NAV_F64, ms * 13 * 8, 13 * 8, n_ch, ms)
+    ip = d_out.cpu().numpy()[:, :, 1]
+    want, wact = O.findTimeMarks("T" * n_ch, ip)
+    assert np.array_equal(first, want) and act == wact == [1, 2, 3]
+    pat = -np.repeat(tm[::-1], 10)
+    for ch in range(n_ch):
+        k0 = int(first[ch]) - 1
+        assert 1500 <= k0 <= 1900  # the first string's mark starts 1.7 s into the record (minus the code phase the tracking starts at)
+        assert abs(int(np.dot(np.sign(ip[ch, k0 + 2000 : k0 + 2300]), pat))) > 290  # and again one string later
