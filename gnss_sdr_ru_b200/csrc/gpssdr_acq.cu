@@ -48,21 +48,43 @@ __device__ __forceinline__ uint32_t cmul_shift(uint32_t a, uint32_t b, int shift
   return pack16(ti, tq);
 }
 
-// In-place 2048-point FFT of the reference (fft.cpp): bit-reversal shuffle, then 11 ranks of 1024 butterflies
-// (bfly / bfly_noscale :401-440).  x: 2048 packed CPX in shared memory, scratch: SCR words, tw: the 1024
-// twiddles (i, q) of W or iW.  rflags bit r = scale rank r by >>1 first.  All threads of the CTA.
-__device__ void fft2048(uint32_t *x, uint32_t *scratch, const uint32_t *__restrict__ tw, unsigned rflags) {
-  const int tid = threadIdx.x;
-  // doShuffle :298-310 (11-bit reversal).  The copy is padded by one word per 32: the bit-reversed read of 32
-  // consecutive l differs only in the high address bits, which would put the whole warp on one bank.
-  for (int l = tid; l < NS; l += NT) scratch[l + (l >> 5)] = x[l];
-  __syncthreads();
-  for (int l = tid; l < NS; l += NT) {
+// 2048-point FFT of the reference (fft.cpp): bit-reversal shuffle (doShuffle :298-310), then 11 ranks of 1024
+// butterflies (bfly / bfly_noscale :401-440).  in: the 2048 packed CPX in natural order, PADDED by one word per 32
+// (element j at in[PAD(j)]) so that the bit-reversed gather below -- 32 consecutive targets differ only in the
+// high source-address bits -- does not land a whole warp on one bank.  x: result, natural order.  tw: the 1024
+// twiddles (i, q) of W or iW.  rflags bit r = scale rank r by >>1 first.  All NT threads of the CTA.
+// Ranks 0-4 only combine elements inside aligned groups of 32: they run in registers, one element per lane, with
+// one warp shuffle per rank; ranks 5-10 go through shared memory (bank-conflict free from there on).
+#define PAD(j) ((j) + ((j) >> 5))
+__device__ __forceinline__ uint32_t bfly_half(uint32_t mine, uint32_t other, bool upper, uint32_t w, bool scale) {
+  // this lane holds A (lower, !upper) or B (upper) of a butterfly; `other` is the partner's element
+  Cpx16 A = unpack16(upper ? other : mine), B = unpack16(upper ? mine : other);
+  const Cpx16 W = unpack16(w);
+  if (scale) {
+    A.i >>= 1; A.q >>= 1; B.i >>= 1; B.q >>= 1;
+  }
+  int bi = (int)B.i * W.i - (int)B.q * W.q, bq = (int)B.i * W.q + (int)B.q * W.i;
+  bi = (bi + 8192) >> 14;
+  bq = (bq + 8192) >> 14;
+  const int16_t sbi = (int16_t)bi, sbq = (int16_t)bq;
+  return upper ? pack16((int16_t)(A.i - sbi), (int16_t)(A.q - sbq)) : pack16((int16_t)(A.i + sbi), (int16_t)(A.q + sbq));
+}
+__device__ void fft2048(const uint32_t *in, uint32_t *x, const uint32_t *__restrict__ tw, unsigned rflags) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int l = tid; l < NS; l += NT) {  // a warp owns the aligned group of 32 around l
     const int src = (int)(__brev((unsigned)l) >> 21);
-    x[l] = scratch[src + (src >> 5)];
+    uint32_t v = in[PAD(src)];
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+      const int bsize = 1 << r;
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, v, bsize);
+      const uint32_t w = __ldg(tw + ((lane & (bsize - 1)) << (10 - r)));
+      v = bfly_half(v, other, (lane >> r) & 1, w, (rflags >> r) & 1);
+    }
+    x[l] = v;
   }
   __syncthreads();
-  for (int r = 0; r < 11; r++) {
+  for (int r = 5; r < 11; r++) {
     const int bsize = 1 << r, nblocks = 1024 >> r;
     const bool scale = (rflags >> r) & 1;
     for (int t = tid; t < 1024; t += NT) {
@@ -90,9 +112,9 @@ __global__ void __launch_bounds__(NT) gsa_prep_kernel(const uint32_t *iq, int ms
   __shared__ uint32_t x[NS], scratch[SCR];
   const int row = blockIdx.x, off = row / ms, m = row % ms, tid = threadIdx.x;
   for (int j = tid; j < NS; j += NT)
-    x[j] = cmul_shift(iq[(size_t)m * NS + j], wipe[(size_t)off * 10 * NS + (m % 10) * NS + j], 14);
+    scratch[PAD(j)] = cmul_shift(iq[(size_t)m * NS + j], wipe[(size_t)off * 10 * NS + (m % 10) * NS + j], 14);
   __syncthreads();
-  fft2048(x, scratch, twf, 0u);  // R1: no rank is scaled
+  fft2048(scratch, x, twf, 0u);  // R1: no rank is scaled
   uint32_t *p = rows + (size_t)row * ROWLEN;
   for (int j = tid; j < ROWLEN - 1; j += NT) p[j] = x[(j + NS - 100) & (NS - 1)];  // 100 wrapped bins on either side
   if (tid == 0) p[ROWLEN - 1] = 0;
@@ -129,9 +151,9 @@ __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, co
   const int l = l0 + combo / 4, l2 = combo % 4, tid = threadIdx.x;
   const uint32_t *code = codes + (size_t)sv_list[svi] * NS;
   const uint32_t *row = rows + (size_t)l2 * ROWLEN + 100 + l;
-  for (int j = tid; j < NS; j += NT) x[j] = cmul_shift(row[j], code[j], 10);
+  for (int j = tid; j < NS; j += NT) scratch[PAD(j)] = cmul_shift(row[j], code[j], 10);
   __syncthreads();
-  fft2048(x, scratch, twi, rflags);
+  fft2048(scratch, x, twi, rflags);
   int mag = 0, idx = 0;
   for (int j = tid; j < NS; j += NT) {
     const Cpx16 c = unpack16(x[j]);
@@ -167,9 +189,9 @@ __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, cons
     for (int l3 = 0; l3 < 10; l3++) {
       const uint32_t *row = rows + (size_t)(l2 * 310 + l3 + i * 20 + k * 10) * ROWLEN + 100 + l;
       uint32_t *x = coh + l3 * NS;
-      for (int j = tid; j < NS; j += NT) x[j] = cmul_shift(row[j], code[j], 9);
+      for (int j = tid; j < NS; j += NT) scratch[PAD(j)] = cmul_shift(row[j], code[j], 9);
       __syncthreads();
-      fft2048(x, scratch, twi, rflags);
+      fft2048(scratch, x, twi, rflags);
     }
     // code-Doppler shift of this round (acquisition.cpp:486-492)
     const double doppler = (double)(l * 1000) + (float)(l2 * 250);
