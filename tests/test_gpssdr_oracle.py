@@ -87,3 +87,40 @@ def test_primitives_match_compiled_reference():
     pr = p.copy()
     R.gsr_max(pr.ctypes.data, C.byref(i2), C.byref(g2), p.size)
     assert (i1.value, g1.value) == (i2.value, g2.value) == (int(np.argmax(p)), int(p.max()))
+
+
+def test_primitives_match_committed_reference_outputs():
+    """same pin without the reference tree: outputs of the reference's compiled primitives committed as
+    tests/golden/gpssdr_ref_golden.npz (made by tests/golden/make_gpssdr_golden.py)"""
+    L = G.lib()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpssdr_ref_golden.npz"))
+    pats = {"R1": np.zeros(16, np.int32), "R2": np.array([0, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 1, 1, 1, 1, 1], np.int32), "Rall": np.ones(16, np.int32)}
+    n = 0
+    for name, Rp in pats.items():
+        for inv in (0, 1):
+            for amp in (60, 20000):
+                x = g[f"fft_{name}_{inv}_{amp}_in"].copy()
+                L.gso_fft(x.ctypes.data, 2048, Rp.ctypes.data, inv, 1)
+                assert np.array_equal(x, g[f"fft_{name}_{inv}_{amp}_out"])
+                n += 1
+    for shift in (9, 10, 14):
+        A, B = g[f"cmulsc_{shift}_a"].copy(), g[f"cmulsc_{shift}_b"].copy()
+        c = np.zeros_like(A)
+        L.gso_cmulsc(A.ctypes.data, B.ctypes.data, c.ctypes.data, A.shape[0], shift)
+        assert np.array_equal(c, g[f"cmulsc_{shift}_c"])
+    for k, f in enumerate((-38400.0, -38650.0, -38900.0, -39150.0)):
+        s = np.zeros((20480, 2), np.int16)
+        L.gso_sine_gen(s.ctypes.data, f, 2048000.0, 20480)
+        assert np.array_equal(s, g[f"sine_{k}"])  # float-phase sinf/cosf of this libm (same image as the reference build)
+    dft = np.zeros((10, 10, 4), np.int16)
+    for r in range(10):
+        L.gso_wipeoff_gen(dft[r].ctypes.data, float(np.float32(r) * 25.0 - 112.5), 1000.0, 10)
+    assert np.array_equal(dft, g["dft_rows"])
+    d, want = g["cacc_in"], g["cacc_out"]
+    for i in range(d.shape[0]):
+        for r in range(10):
+            a, b = C.c_int32(), C.c_int32()
+            di = np.ascontiguousarray(d[i])
+            L.gso_cacc(di.ctypes.data, dft[r].ctypes.data, 10, C.byref(a), C.byref(b))
+            assert (a.value, b.value) == tuple(want[i, r])
+    assert n == 12
