@@ -216,6 +216,13 @@ class IngestStat(C.Structure):
                 ("blocks_done", C.c_int64), ("finished", C.c_int32), ("overflow", C.c_int32)]
 
 
+class SerialCell(C.Structure):
+    _fields_ = [("prn", C.c_int16), ("n_freq", C.c_int16), ("codes", C.c_int32), ("ip", C.c_int32), ("qp", C.c_int32), ("rss", C.c_int32)]
+
+
+SERIAL_CELL_DTYPE = [("prn", "<i2"), ("n_freq", "<i2"), ("codes", "<i4"), ("ip", "<i4"), ("qp", "<i4"), ("rss", "<i4")]
+
+
 class GpsSdrResult(C.Structure):
     _fields_ = [("sv", C.c_int32), ("type", C.c_int32), ("code_phase", C.c_int32), ("doppler", C.c_int32), ("magnitude", C.c_uint32),
                 ("success", C.c_int32)]

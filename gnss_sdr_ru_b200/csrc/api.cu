@@ -201,6 +201,78 @@ extern "C" int gnssb200_download_rx(gnssb200_handle *h, int first, int count, gn
   return 0;
 }
 
+// Serial search as a cell map: a private handle with the detection threshold out of reach, one channel per PRN, the
+// shared record read with stride 0 by every receiver, then the dump records turned into cells (the record of dump
+// k carries the bin / delay the channel moved to AFTER that dump, so cell k is described by record k-1).
+extern "C" int gnssb200_acq_serial(gnssb200_handle *h, const void *d_if, int fmt, int64_t n_samples, const int32_t *prn_list, int n_prn,
+                                   int search_max_f, int max_prn_delay, gnssb200_serial_cell *cells, int cells_cap, int32_t *n_cells) {
+  if (!h || !d_if || !prn_list || n_prn <= 0 || !cells || cells_cap <= 0 || !n_cells || n_samples < 8192) {
+    gnssb200_set_error(-8, "gnssb200_acq_serial: bad arguments", __FILE__, __LINE__);
+    return -8;
+  }
+  gnssb200_cfg cfg = h->cfg;
+  cfg.acq_thresh = 0x7fffffff;
+  gnssb200_handle *t = gnssb200_open(h->device, &cfg);
+  if (!t) return gnssb200_last_error();
+  const int S = (n_prn + NCH - 1) / NCH, nsamp = 8192;
+  const long long nblocks = n_samples / nsamp;
+  const int dump_cap = cells_cap + 1;
+  int rc = gnssb200_set_streams(t, S);
+  std::vector<gnssb200_rx> rx(S);
+  for (int s = 0; s < S && !rc; s++) {
+    int32_t prn[NCH];
+    for (int c = 0; c < NCH; c++) prn[c] = (s * NCH + c < n_prn) ? prn_list[s * NCH + c] : 0;
+    gnssb200_rx_init(&rx[s], &cfg);
+    gnssb200_rx_cold_allocate(&rx[s], &cfg, prn);
+    for (int c = 0; c < NCH; c++) {
+      rx[s].chan[c].search_max_f = search_max_f;
+      rx[s].chan[c].search_max_PRN_delay = max_prn_delay > 0 ? max_prn_delay : 2045;
+    }
+  }
+  if (!rc) rc = gnssb200_upload_rx(t, 0, S, rx.data());
+  gnssb200_dump *d_dumps = nullptr;
+  int32_t *d_cnt = nullptr;
+  std::vector<gnssb200_dump> dumps((size_t)S * NCH * dump_cap);
+  std::vector<int32_t> cnt((size_t)S * NCH);
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaMalloc(&d_dumps, dumps.size() * sizeof(gnssb200_dump));
+  if (!rc && e == cudaSuccess) e = cudaMalloc(&d_cnt, cnt.size() * sizeof(int32_t));
+  if (!rc && e == cudaSuccess) e = cudaMemset(d_cnt, 0, cnt.size() * sizeof(int32_t));
+  if (!rc && e == cudaSuccess) rc = gnssb200_track_run(t, d_if, 0 /* every receiver reads the same record */, fmt, nsamp, nblocks, d_dumps, dump_cap, d_cnt, nullptr);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(dumps.data(), d_dumps, dumps.size() * sizeof(gnssb200_dump), cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(cnt.data(), d_cnt, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess) {
+    h->launches += t->launches;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t->ev0, t->ev1) == cudaSuccess) h->serial_ms = ms;
+  }
+  cudaFree(d_dumps);
+  cudaFree(d_cnt);
+  gnssb200_close(t);
+  if (e != cudaSuccess) {
+    gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    return (int)e;
+  }
+  if (rc) return rc;
+  for (int p = 0; p < n_prn; p++) {
+    const gnssb200_dump *d = &dumps[(size_t)p * dump_cap];
+    const int n = cnt[p] < dump_cap ? cnt[p] : dump_cap;
+    int k = 0;
+    for (int i = 1; i < n && k < cells_cap; i++, k++) {
+      gnssb200_serial_cell &c = cells[(size_t)p * cells_cap + k];
+      c.prn = (int16_t)prn_list[p];
+      c.n_freq = d[i - 1].n_freq;
+      c.codes = d[i - 1].codes;
+      c.ip = d[i].acc[2];
+      c.qp = d[i].acc[3];
+      const long long a = c.ip < 0 ? -(long long)c.ip : c.ip, b = c.qp < 0 ? -(long long)c.qp : c.qp;
+      c.rss = (int32_t)(a > b ? a + (b >> 1) : b + (a >> 1));  // rss(), osgpsisr.c:77-91
+    }
+    n_cells[p] = k;
+  }
+  return 0;
+}
+
 extern "C" int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks) {
   if (!h || blocks < 0) return -1;
   h->track_slice = blocks;

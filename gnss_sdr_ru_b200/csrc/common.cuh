@@ -33,6 +33,7 @@ struct gnssb200_handle {
   uint32_t *d_code_table;     // [TABLE_ENTRIES+1] packed E | P<<8 | L<<16 (int8 each), last entry 0
   cudaEvent_t ev0, ev1;
   long long launches;
+  float serial_ms;            // device time of the last gnssb200_acq_serial run
   // acquisition workspace (acq.cu)
   void *acq_ws;
   // staging of gnssb200_track_run_host (api.cu), kept between calls

@@ -174,6 +174,19 @@ class TrackingEngine:
         return float(self.L.gnssb200_last_kernel_ms(self.h))
 
 
+def acq_serial(handle, d_if_ptr: int, fmt: int, n_samples: int, prn_list, search_max_f: int = 5, max_prn_delay: int = 2045,
+               cells_cap: int = 4096):
+    """gnssb200_acq_serial: exhaustive GP2021-semantics serial-search cell map of a device-resident record.
+    Returns {prn: structured array of (prn, n_freq, codes, ip, qp, rss)}."""
+    L = lib()
+    prn = np.ascontiguousarray(prn_list, dtype=np.int32)
+    cells = np.zeros((len(prn), cells_cap), dtype=abi.SERIAL_CELL_DTYPE)
+    n = np.zeros(len(prn), dtype=np.int32)
+    check(L.gnssb200_acq_serial(handle, d_if_ptr, fmt, n_samples, prn.ctypes.data, len(prn), search_max_f, max_prn_delay, cells.ctypes.data,
+                                cells_cap, n.ctypes.data), "gnssb200_acq_serial")
+    return {int(p): cells[i, : n[i]].copy() for i, p in enumerate(prn)}
+
+
 def serial_search_cell_map(dumps: np.ndarray, counts: np.ndarray):
     """Turn the dump records of a run with the detection threshold out of reach into the GP2021-semantics
     search cell map {(stream, channel): array of (n_freq, code delay in half chips, IP, QP, rss)}.

@@ -181,6 +181,21 @@ int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stream_
                             int nsamp, int64_t nblocks, gnssb200_dump *h_dumps, int dump_cap,
                             int32_t *h_dump_count);
 
+/* GP2021-semantics serial search as an exhaustive cell map: every PRN of prn_list gets a channel that
+ * searches like ch_acq (OSG/isr/osgpsisr.c:424-459) with the detection threshold out of reach -- 2045 (or
+ * max_prn_delay) half-chip code delays per Doppler bin, bins 0,+1,-1,+2,... up to +-search_max_f of width
+ * cfg.freq_bin_width -- over the whole device-resident record (fmt INT8_IQ or PACKED2, n_samples complex samples, 8192
+ * per block).  One dump = one cell: cells[p*cells_cap + k] describes the k-th cell of prn_list[p]
+ * (the bin / delay the channel was in, the prompt sums of that dump and rss(IP,QP), osgpsisr.c:77-91);
+ * n_cells[p] = cells completed (at most cells_cap are stored).  The handle's own receivers are not touched. */
+typedef struct gnssb200_serial_cell {
+  int16_t prn, n_freq;      /* PRN, Doppler bin index (carrier = gps_carrier_ref + n_freq * d_freq) */
+  int32_t codes;            /* code delay in half chips */
+  int32_t ip, qp, rss;
+} gnssb200_serial_cell;
+int gnssb200_acq_serial(gnssb200_handle *h, const void *d_if, int fmt, int64_t n_samples, const int32_t *prn_list, int n_prn,
+                        int search_max_f, int max_prn_delay, gnssb200_serial_cell *cells, int cells_cap, int32_t *n_cells);
+
 /* Scheduling knob of the tracking kernel: the blocks of every channel are cut into slices of `blocks`
  * blocks that are handed to CTAs through a work queue (keeps all SMs busy whatever the channel count).
  * 0 = automatic (slices of 128 blocks -- 512 KB of packed samples, so the slices in flight stay L2 resident -- from four channels per SM on, one slice per channel below).  Results do

@@ -41,14 +41,14 @@ def test_struct_layouts_match_header():
     src = r'''
 #include <stdio.h>
 #include "gnssb200.h"
-int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",sizeof(gnssb200_cfg),sizeof(gnssb200_chan),sizeof(gnssb200_corr),
- sizeof(gnssb200_rx),sizeof(gnssb200_dump),sizeof(gnssb200_acq_cfg),sizeof(gnssb200_acq_row),sizeof(gnssb200_acq_result),sizeof(gnssb200_synth_sat),sizeof(gnssb200_softtrack_cfg),sizeof(gnssb200_softtrack_chan),sizeof(gnssb200_ingest_stat),sizeof(gnssb200_gpssdr_result));return 0;}
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",sizeof(gnssb200_cfg),sizeof(gnssb200_chan),sizeof(gnssb200_corr),
+ sizeof(gnssb200_rx),sizeof(gnssb200_dump),sizeof(gnssb200_acq_cfg),sizeof(gnssb200_acq_row),sizeof(gnssb200_acq_result),sizeof(gnssb200_synth_sat),sizeof(gnssb200_softtrack_cfg),sizeof(gnssb200_softtrack_chan),sizeof(gnssb200_ingest_stat),sizeof(gnssb200_gpssdr_result),sizeof(gnssb200_serial_cell));return 0;}
 '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         out = subprocess.check_output([os.path.join(d, "s")]).split()
-    want = [C.sizeof(x) for x in (abi.Cfg, abi.Chan, abi.Corr, abi.Rx, abi.Dump, abi.AcqCfg, abi.AcqRow, abi.AcqResult, abi.SynthSat, abi.SoftTrackCfg, abi.SoftTrackChan, abi.IngestStat, abi.GpsSdrResult)]
+    want = [C.sizeof(x) for x in (abi.Cfg, abi.Chan, abi.Corr, abi.Rx, abi.Dump, abi.AcqCfg, abi.AcqRow, abi.AcqResult, abi.SynthSat, abi.SoftTrackCfg, abi.SoftTrackChan, abi.IngestStat, abi.GpsSdrResult, abi.SerialCell)]
     assert [int(x) for x in out] == want
 
 

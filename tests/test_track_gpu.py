@@ -263,3 +263,38 @@ def test_serial_search_bin_stepping(oracle_lib, track_record):
     assert set(np.unique(d0["n_freq"])) == {-2, -1, 0, 1, 2, 3}
     assert (np.diff(np.nonzero(d0["n_freq"] == 3)[0]) > 1).all()
     assert (d0["state"] == 1).all()
+
+
+def test_acq_serial_cell_map_equals_oracle_search(oracle_lib, track_record):
+    """gnssb200_acq_serial (C ABI): 14 PRNs (two receivers on one shared record), +-2 bins of 500 Hz, 60 code delays per
+    bin -- every cell (bin, delay, IP, QP, rss) equals what the oracle's ch_acq sweep produces, and the satellite that is
+    in the record stands out at its own bin / delay."""
+    import torch
+
+    from gnss_sdr_ru_b200.lib import default_cfg
+    from gnss_sdr_ru_b200.receiver import TrackingEngine, acq_serial, serial_search_cell_map
+
+    rec, _ = track_record
+    nblk = 1500
+    over = dict(freq_bin_width=500.0)
+    eng = TrackingEngine(n_streams=1, cfg=default_cfg(**over))
+    prns = [27, 9, 32, 1, 2, 3, 4, 5, 6, 7, 8, 31, 11, 12]
+    d = torch.from_numpy(rec[: 2 * NS * nblk].view(np.uint8).copy()).cuda()
+    got = acq_serial(eng.h, d.data_ptr(), abi.FMT_INT8_IQ, NS * nblk, prns, search_max_f=2, max_prn_delay=60, cells_cap=800)
+    for s in range(2):
+        o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(acq_thresh=2**31 - 1, **over))
+        sub = (prns[12 * s : 12 * s + 12] + [0] * 12)[:12]
+        o.cold_allocate(sub)
+        for ch in range(12):
+            o.rx.chan[ch].search_max_PRN_delay = 60
+            o.rx.chan[ch].search_max_f = 2
+        _, od, oc = o.run(rec[: 2 * NS * nblk], NS, nblk, dump_cap=801)
+        want = serial_search_cell_map(od[None], oc[None])
+        for ch, prn in enumerate(sub):
+            if prn == 0:
+                continue
+            w = want[(0, ch)]
+            g = got[prn]
+            assert len(g) == len(w) > 700
+            assert np.array_equal(np.stack([g["n_freq"], g["codes"], g["ip"], g["qp"], g["rss"]], axis=1).astype(np.int64), w)
+    assert set(np.unique(got[27]["n_freq"])) == {-2, -1, 0, 1, 2, 3}  # 3 = the overflow value before the restart
