@@ -3,32 +3,29 @@
 // What it replaces: Sim_GP2021_int (OSG/correlator/correlator.c:148-316) followed by gpsisr
 // (OSG/isr/osgpsisr.c:360-408) once per 512 us block, for S independent IF streams x 12 channels.
 //
-// Mapping (B200): one CTA per (stream, channel).  Channels of a receiver never exchange data in
-// the reference (each dump only touches its own registers and its own struct tracking_channel), so
-// a CTA runs its channel through all blocks without any grid-wide synchronisation:
+// Two kernels share the arithmetic below (closed-form NCO starts, grouped code taps, dump rules, device ISR):
 //
-//   staging:    the block's samples are brought into shared memory by the TMA engine
-//               (cp.async.bulk + mbarrier, one elected thread), double buffered: block b+1 lands
-//               while block b is correlated and its ISR runs.  Packed 2-bit input is 4 KB per block.
-//   per block:  every thread takes 32 consecutive complex samples (128-bit shared-memory loads),
-//               starts its carrier/code NCOs from the closed form phase(i) = phase0 + i*incr
-//               (SURVEY.md Appendix A), and walks them with the exact integer arithmetic of the
-//               reference: 8-phase LO (phase>>29), complex mix, +-1 E/P/L taps at half-chip spacing.
-//               I and Q products ride in one 32-bit register as two 16-bit lanes (|sum| <= 32*384
-//               per thread).  Samples are taken four at a time: with 4*kinc < 2^32 at most one
-//               code-NCO carry falls inside a group, so the group contributes
-//               old_bits*S_old + new_bits*S_new  -- 6 IMADs and one table read per 4 samples instead
-//               of 12 IMADs and 4 predicated reloads.
-//   dump:       at most one per block on this path; a chunk lies before, after or across it.  The
-//               (single) straddling chunk is re-evaluated sample-per-lane by its warp with the
-//               closed forms, so no thread carries two accumulator sets through its loop.
-//   reduce:     warp shuffles, then twelve shared-memory atomics per warp.
-//   ISR:        lane 0 of warp 0 applies the dump / TIC / epoch rules, runs the channel state
-//               machine (isr_device.cuh) and publishes next block's NCO words.
+//   track_ws_kernel    the hot path (8192-sample blocks or shorter, 16-byte aligned, int8 I,Q or packed 2+2 bit):
+//                      warp-specialised -- correlator warps + one control lane per CTA, decoupled by mbarriers,
+//                      samples staged by the TMA engine, ISR bookkeeping after the next block's parameters are
+//                      published -- and scheduled through a (channel, time-slice) work queue.  Described where
+//                      it is defined.
+//   track_loop_kernel  the generic variant (any block length, unaligned or ragged records, I-only input; also
+//                      selectable with GNSSB200_TRACK_WS=0 for A/B runs): one CTA per (stream, channel) for the
+//                      whole run, barrier-synchronised: TMA double buffering, 32 samples per thread per pass,
+//                      warp-shuffle + shared-atomic reduction, lane 0 of warp 0 as the ISR lane.
 //
-// Register values the fast path cannot express (a second dump inside one block, half-chip counts
-// beyond two table rows, PRN outside 1..32, ...) take the serial path: lane 0 walks the block
-// with the literal per-sample loop.  It is still device code; there is no CPU fallback.
+// Per block, both: every thread takes consecutive complex samples, starts its carrier/code NCOs from the closed
+// form phase(i) = phase0 + i*incr and walks them with the exact integer arithmetic of the
+// reference: 8-phase LO (phase>>29), complex mix, +-1 E/P/L taps at half-chip spacing.  I and Q products ride in
+// one 32-bit register as two 16-bit lanes.  Samples go four at a time: with 4*kinc < 2^32 at most one code-NCO
+// carry falls inside a group, so the group contributes old_bits*S_old + new_bits*S_new -- 6 IMADs and one table
+// read per 4 samples.  At most one dump per block on this path; the single straddling chunk is re-evaluated
+// sample-per-lane by its warp from the closed forms.
+//
+// Register values the fast path cannot express (a second dump inside one block, slews beyond the table window,
+// PRN outside 1..32, ...) take the serial path: one lane walks the block with the literal per-sample loop.  It is
+// still device code; there is no CPU fallback.
 #include "isr_device.cuh"
 
 #define MODE_STOP (-1)
@@ -605,7 +602,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
 
   const int s = a.first_stream + blockIdx.x / NCH, ch = blockIdx.x % NCH;
   gnssb200_rx *rx = a.rx + s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tbl_prn = rx->reg_write[ch << 3];
 
   fill_lo_lut(lut);
@@ -1115,7 +1112,7 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t blk_bytes = bytes_for(fmt, a.nsamp);
   constexpr int CTRL = WS_CORR_THREADS;  // the control lane
-  SchedQueue *const q = a.sched;
+  SchedQueue *const wq = a.sched;
   // channel-independent tables first: they fill while the control lane may still be waiting for its item
   fill_lo_lut(lut);
   if (packed_native) {
@@ -1130,8 +1127,8 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
     }
   }
   if (tid == CTRL) {  // this CTA's item
-    const unsigned ticket = atomicAdd(&q->head, 1u);
-    volatile SchedSlot *slot = q->slots + ticket % q->nchan;
+    const unsigned ticket = atomicAdd(&wq->head, 1u);
+    volatile SchedSlot *slot = wq->slots + ticket % wq->nchan;
     unsigned long long v;
     while ((unsigned)(v = *slot) != ticket) __nanosleep(100);
     __threadfence();  // acquire: the state the previous slice of this channel stored
@@ -1139,12 +1136,12 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   }
   __syncthreads();
   const int item = s_item;
-  const int chan_id = item % (int)q->nchan, slice = item / (int)q->nchan;
+  const int chan_id = item % (int)wq->nchan, slice = item / (int)wq->nchan;
   const int s = a.first_stream + chan_id / NCH, ch = chan_id % NCH;
   gnssb200_rx *rx = a.rx + s;
   const int tbl_prn = __ldcg(&rx->reg_write[ch << 3]);
-  const long long slice_first = (long long)slice * q->slice_blocks;          // first block of this slice within the launch
-  const long long nblocks = min(q->slice_blocks, a.nblocks - slice_first);    // blocks of this slice
+  const long long slice_first = (long long)slice * wq->slice_blocks;          // first block of this slice within the launch
+  const long long nblocks = min(wq->slice_blocks, a.nblocks - slice_first);    // blocks of this slice
   const uint8_t *stream_base = a.d_if + (size_t)s * a.stride + (size_t)slice_first * blk_bytes;
 
   if (tid < 12) totals[tid] = 0;
@@ -1175,10 +1172,10 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
     for (int j = 0; j < 8; j++) cs.r.r_meas[j] = __ldcg(&rx->reg_read[b8 + j]);
     for (int j = 0; j < 6; j++) cs.r.r_acc[j] = __ldcg(&rx->reg_read[b8 + 0x84 + j]);
     const int prev_flags = slice > 0 ? __ldcg(&a.chan_flags[s * NCH + ch]) : 0;
-    cs.tic = slice > 0 ? __ldcg(&q->tic[chan_id]) : rx->tic;
+    cs.tic = slice > 0 ? __ldcg(&wq->tic[chan_id]) : rx->tic;
     cs.dumped_last = prev_flags & 1;
     cs.halted = (prev_flags >> 1) & 1;
-    cs.dump_count = a.dump_count ? __ldcg(&a.dump_count[s * NCH + ch]) : (slice > 0 ? __ldcg(&q->dumpcnt[chan_id]) : 0);
+    cs.dump_count = a.dump_count ? __ldcg(&a.dump_count[s * NCH + ch]) : (slice > 0 ? __ldcg(&wq->dumpcnt[chan_id]) : 0);
     first_block = rx->blocks_done + slice_first;
     sp.stale_bits = 0;
     if (nblocks > 0 && !rx->halted && !cs.halted) {
@@ -1357,18 +1354,16 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
     if (a.dump_count)
       a.dump_count[s * NCH + ch] = cs.dump_count;
     else
-      q->dumpcnt[chan_id] = cs.dump_count;
-    q->tic[chan_id] = cs.tic;
-    const unsigned next_item = (unsigned)item + q->nchan;  // the channel's next slice
-    if (next_item < q->total) {
+      wq->dumpcnt[chan_id] = cs.dump_count;
+    wq->tic[chan_id] = cs.tic;
+    const unsigned next_item = (unsigned)item + wq->nchan;  // the channel's next slice
+    if (next_item < wq->total) {
       __threadfence();  // release: the state stored above, before the item becomes visible
-      const unsigned t = atomicAdd(&q->tail, 1u);
-      atomicExch(q->slots + t % q->nchan, (unsigned long long)t | ((unsigned long long)next_item << 32));
+      const unsigned t = atomicAdd(&wq->tail, 1u);
+      atomicExch(wq->slots + t % wq->nchan, (unsigned long long)t | ((unsigned long long)next_item << 32));
     }
     return;
   }
-  (void)first_block;
-  (void)loaded;
 
   // ---------------- correlator warps ----------------
   const int i0 = tid * SPT;
