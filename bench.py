@@ -425,6 +425,29 @@ def run_ours(args):
                                             "cells_per_s": cells3 / (ms3 * 1e-3),
                                             "note": "threshold out of reach, 500 Hz bins, search_max_f=20; reference C receiver: ~18e3 cells/s per core"}
         eng3.close()
+        # drop-in layer: the reference's own call, Sim_GP2021_int(IF, 8192) with a host buffer, synchronous (one H2D, one
+        # 12-CTA launch, one register-file read-back per 512 us of signal) -- what the unchanged C receiver gets
+        try:
+            from gnss_sdr_ru_b200.receiver import DropInCorrelator
+
+            dc = DropInCorrelator()
+            for c_, p_ in enumerate([27, 9, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31]):
+                dc.ch_cntl(c_, p_)
+                dc.ch_carrier(c_, int(eng.cfg.gps_carrier_ref))
+                dc.ch_code(c_, int(eng.cfg.gps_code_ref))
+            one = np.ascontiguousarray((np.arange(2 * NS) % 4 * 2 - 3).astype(np.int8))
+            for _ in range(50):
+                dc.Sim_GP2021_int(one, NS)
+            ncall = 2000
+            t0 = time.perf_counter()
+            for _ in range(ncall):
+                dc.Sim_GP2021_int(one, NS)
+            dtc = (time.perf_counter() - t0) / ncall
+            also["dropin_Sim_GP2021_int_host_call"] = {"us_per_call": dtc * 1e6, "channel_Msamples_per_s": 12 * NS / dtc / 1e6,
+                                                       "real_time_factor": 512e-6 / dtc,
+                                                       "note": "synchronous per-block call of the reference's own entry point (12 channels); the reference C code needs ~435 us per call on one core"}
+        except Exception as ex:
+            also["dropin_Sim_GP2021_int_host_call"] = {"error": repr(ex)}
         # floating-point (Scilab) tracking, 8 GLONASS channels x 2 s, FP64
         from gnss_sdr_ru_b200.softtrack import SoftTrackingEngine, TrackSettings
         from gnss_sdr_ru_b200.scenarios import TrackScenario
