@@ -171,7 +171,9 @@ int gnssb200_download_rx(gnssb200_handle *h, int first, int count, gnssb200_rx *
  *                 [(s*12+ch)*dump_cap + k]
  *   d_dump_count  device int32[n_streams*12], number of records written per channel (may be NULL)
  *   cuda_stream   a cudaStream_t passed as void* (NULL = default stream).  Asynchronous.
- * Blocks continue from the state left by the previous call (rx.blocks_done advances). */
+ * Blocks continue from the state left by the previous call (rx.blocks_done advances).  Calls on one handle must
+ * be ordered (same CUDA stream, or synchronised by the caller); only runs on disjoint receivers issued through
+ * gnssb200_ingest_* may overlap. */
 int gnssb200_track_run(gnssb200_handle *h, const void *d_if, size_t stream_stride_bytes, int fmt,
                        int nsamp, int64_t nblocks, gnssb200_dump *d_dumps, int dump_cap,
                        int32_t *d_dump_count, void *cuda_stream);
