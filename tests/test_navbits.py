@@ -249,3 +249,54 @@ def test_chain_glonass_acquisition_tracking_time_marks_on_device():
         k0 = int(first[ch]) - 1
         assert 1500 <= k0 <= 1900  # the first string's mark starts 1.7 s into the record (minus the code phase the tracking starts at)
         assert abs(int(np.dot(np.sign(ip[ch, k0 + 2000 : k0 + 2300]), pat))) > 290  # and again one string later
+
+
+@pytest.mark.gpu
+def test_chain_gps_scilab_acquisition_tracking_preambles_on_device():
+    """The GPS Scilab chain on the GPU: 12.6 s record with parity-correct subframes synthesised on the device,
+    acquisition -> preRun -> floating-point tracking (results stay in HBM) -> findPreambles on the I_P field.
+    Indices equal the oracle's on the downloaded buffer; the subframe start is where the signal put it."""
+    import ctypes as C
+
+    import torch
+
+    from gnss_sdr_ru_b200 import abi
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.lib import check, lib
+    from gnss_sdr_ru_b200.navbits import NAV_F64, NavBitsEngine
+    from gnss_sdr_ru_b200.scenarios import TrackScenario, synth_sat_array
+    from gnss_sdr_ru_b200.softtrack import SoftTrackingEngine, TrackSettings, preRun
+    from gnss_sdr_ru_b200.synth import Sat
+
+    rng = np.random.default_rng(44)
+    ms = 12600
+    sats = []
+    for i, (prn, dop) in enumerate(((6, 2150.0), (21, -3320.0))):
+        bits = O.gps_nav_bits(3, rng).astype(np.uint8)
+        sats.append(Sat(prn=prn, cn0_dbhz=48.0, doppler_hz=dop, code_phase_chips=250.0 + 301.0 * i, data_bits=bits))
+    L = lib()
+    acq_eng = AcquisitionEngine()
+    n = 16000 * (ms + 20)
+    d_rec = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    arr, nsat = synth_sat_array([TrackScenario(sats=sats, prns=[], n_freq=[])])
+    check(L.gnssb200_synth(acq_eng.h, d_rec.data_ptr(), 2 * n, abi.FMT_INT8_IQ, 1, n, C.addressof(arr), nsat, 1212, None), "synth")
+    st = Settings.gps(acqSearchBand=14.0, acqCohIntegration=4, acqSatelliteList=[6, 13, 21])
+    head = d_rec[: 2 * 16000 * 9].cpu().numpy().view(np.int8)
+    acq = acq_eng.acquisition(head, st)
+    ts = TrackSettings.gps(msToProcess=ms)
+    channel = preRun(acq, ts)
+    assert sorted(c["FCH"] for c in channel) == [6, 21]
+    n_ch = len(channel)
+    d_out = torch.zeros((n_ch, ms, 13), dtype=torch.float64, device="cuda")
+    d_done = torch.zeros(n_ch, dtype=torch.int32, device="cuda")
+    SoftTrackingEngine(handle=acq_eng.h).tracking_device(d_rec.data_ptr(), n, channel, ts, d_out.data_ptr(), d_done.data_ptr())
+    assert d_done.cpu().tolist() == [ms] * n_ch
+    nav = NavBitsEngine(handle=acq_eng.h)
+    first, act = nav.findPreambles_device(d_out.data_ptr() + 8, NAV_F64, ms * 13 * 8, 13 * 8, n_ch, ms)
+    ip = d_out.cpu().numpy()[:, :, 1]
+    want, wact = O.findPreambles("T" * n_ch, ip)
+    assert np.array_equal(first, want) and act == wact == [1, 2]
+    # subframes start every 6000 ms of signal; the first one after the 5000 ms search offset is the second (6000 ms),
+    # seen from where the tracking started (the acquired code phase, < 1 ms into the record)
+    for ch in range(n_ch):
+        assert 5995 <= int(first[ch]) <= 6002, first
