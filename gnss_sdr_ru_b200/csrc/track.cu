@@ -1126,7 +1126,9 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
       vlut[i] = (uint32_t)(ival + 65536 * qval);
     }
   }
-  if (tid == CTRL) {  // this CTA's item
+  // One item per channel (few channels, or a short run): no queue at all, the CTA index is the channel.
+  const bool queued = wq != nullptr;
+  if (queued && tid == CTRL) {  // this CTA's item
     const unsigned ticket = atomicAdd(&wq->head, 1u);
     volatile SchedSlot *slot = wq->slots + ticket % wq->nchan;
     unsigned long long v;
@@ -1135,13 +1137,15 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
     s_item = (int)(v >> 32);
   }
   __syncthreads();
-  const int item = s_item;
-  const int chan_id = item % (int)wq->nchan, slice = item / (int)wq->nchan;
+  const int item = queued ? s_item : (int)blockIdx.x;
+  const int nchan = queued ? (int)wq->nchan : (int)gridDim.x;
+  const long long slice_blocks = queued ? wq->slice_blocks : a.nblocks;
+  const int chan_id = item % nchan, slice = item / nchan;
   const int s = a.first_stream + chan_id / NCH, ch = chan_id % NCH;
   gnssb200_rx *rx = a.rx + s;
   const int tbl_prn = __ldcg(&rx->reg_write[ch << 3]);
-  const long long slice_first = (long long)slice * wq->slice_blocks;          // first block of this slice within the launch
-  const long long nblocks = min(wq->slice_blocks, a.nblocks - slice_first);    // blocks of this slice
+  const long long slice_first = (long long)slice * slice_blocks;          // first block of this slice within the launch
+  const long long nblocks = min(slice_blocks, a.nblocks - slice_first);    // blocks of this slice
   const uint8_t *stream_base = a.d_if + (size_t)s * a.stride + (size_t)slice_first * blk_bytes;
 
   if (tid < 12) totals[tid] = 0;
@@ -1351,13 +1355,13 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
     for (int q = 1; q < 8; q++) rx->reg_read[b8 + q] = cs.r.r_meas[q];
     for (int q = 0; q < 6; q++) rx->reg_read[b8 + 0x84 + q] = cs.r.r_acc[q];
     a.chan_flags[s * NCH + ch] = (cs.dumped_last ? 1 : 0) | (cs.halted ? 2 : 0);
-    if (a.dump_count)
-      a.dump_count[s * NCH + ch] = cs.dump_count;
-    else
-      wq->dumpcnt[chan_id] = cs.dump_count;
-    wq->tic[chan_id] = cs.tic;
-    const unsigned next_item = (unsigned)item + wq->nchan;  // the channel's next slice
-    if (next_item < wq->total) {
+    if (a.dump_count) a.dump_count[s * NCH + ch] = cs.dump_count;
+    if (queued) {
+      if (!a.dump_count) wq->dumpcnt[chan_id] = cs.dump_count;
+      wq->tic[chan_id] = cs.tic;
+    }
+    const unsigned next_item = (unsigned)item + (unsigned)nchan;  // the channel's next slice
+    if (queued && next_item < wq->total) {
       __threadfence();  // release: the state stored above, before the item becomes visible
       const unsigned t = atomicAdd(&wq->tail, 1u);
       atomicExch(wq->slots + t % wq->nchan, (unsigned long long)t | ((unsigned long long)next_item << 32));
@@ -1716,10 +1720,12 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     long long *tic = reinterpret_cast<long long *>(base + sizeof(SchedQueue) * (size_t)h->n_streams) + (size_t)first_stream * NCH;
     SchedSlot *slots = reinterpret_cast<SchedSlot *>(base + sizeof(SchedQueue) * (size_t)h->n_streams + 8 * n_all) + (size_t)first_stream * NCH;
     int32_t *dcnt = reinterpret_cast<int32_t *>(base + sizeof(SchedQueue) * (size_t)h->n_streams + 16 * n_all) + (size_t)first_stream * NCH;
-    sched_init_kernel<<<(grid + 255) / 256, 256, 0, st>>>(qd, (unsigned)grid, nslices, slice_blocks, tic, dcnt, slots);
-    CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
-    a.sched = qd;
+    if (nslices > 1) {
+      sched_init_kernel<<<(grid + 255) / 256, 256, 0, st>>>(qd, (unsigned)grid, nslices, slice_blocks, tic, dcnt, slots);
+      CUDA_TRY(cudaGetLastError());
+      h->launches += 1;
+      a.sched = qd;
+    }
     const unsigned items = (unsigned)grid * nslices;
     // CTAs per SM the channels ask for -> variant (registers / samples per thread)
     const int per_sm = force_occ ? force_occ : (grid + sms - 1) / sms;
