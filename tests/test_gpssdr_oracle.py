@@ -124,3 +124,41 @@ def test_primitives_match_committed_reference_outputs():
             L.gso_cacc(di.ctypes.data, dft[r].ctypes.data, 10, C.byref(a), C.byref(b))
             assert (a.value, b.value) == tuple(want[i, r])
     assert n == 12
+
+
+def test_restated_pipeline_finds_planted_satellites():
+    """doPrepIF + doAcqStrong / doAcqWeak of the restatement on a synthetic 2.048 Msps record: the planted
+    satellites come out at their code phase and Doppler, absent ones stay far below."""
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    rng = np.random.default_rng(8)
+    chips = gpssdr_codes.prn_gen()
+    codes = gpssdr_codes.fft_codes()
+
+    def record(ms, sats):
+        n = ms * 2048
+        t = np.arange(n) / 2048000.0
+        x = 8.0 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        for sv, amp, dopp, off in sats:
+            ci = (np.floor((np.arange(n) + off) * 1023.0 / 2048.0)).astype(np.int64) % 1023
+            x += amp * chips[ci, sv] * np.exp(2j * np.pi * (38400.0 + dopp) * t)
+        out = np.empty((n, 2), dtype=np.int16)
+        out[:, 0], out[:, 1] = np.round(x.real), np.round(x.imag)
+        return out
+
+    o = G.GpsSdrAcquisition(fif=38400.0)
+    try:
+        rec1 = record(1, [(4, 4.0, 1500.0, 700)])
+        o.doPrepIF(0, rec1)
+        s = o.doAcqStrong(codes[4], -4000, 4000)
+        a = o.doAcqStrong(codes[9], -4000, 4000)
+        assert s["code_phase"] == 700 and abs(s["doppler"] - 1500) <= 250 and s["magnitude"] > 4 * a["magnitude"]
+        rec = record(310, [(4, 0.5, 1500.0, 700)])
+        o.doPrepIF(2, rec)
+        w = o.doAcqWeak(codes[4], 1000, 2000)
+        b = o.doAcqWeak(codes[9], 1000, 2000)
+        # doAcqWeak reports the index of the power matrix column: (2048 - offset) % 2048 like the strong search's raw index
+        assert w["code_phase"] in (2048 - 700, 2048 - 701, 2048 - 699) and abs(w["doppler"] - 112.5 - 1500) <= 50
+        assert w["magnitude"] > 5 * b["magnitude"]
+    finally:
+        o.close()
