@@ -1699,6 +1699,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       aws = true;
     }
     // Work queue: every channel's blocks are cut into slices of slice_blocks; one CTA per (channel, slice)
@@ -1733,8 +1734,10 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
       track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
-    else if (per_sm >= 5)
+    else if (force_occ == 6)
       track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
+    else if (per_sm >= 5)  // five resident CTAs of 72 registers beat six of 64 (spills) by 1-4 % under the work queue
+      track_ws_kernel<5, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm == 4)
       track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm == 3)
