@@ -5,6 +5,9 @@
 //   Acquisition::doPrepIF      RT/objects/acquisition.cpp:182-236   250/500/750 Hz offsets, mix to baseband,
 //                                                                   forward FFT of every millisecond, padded rows
 //   Acquisition::doAcqStrong   RT/objects/acquisition.cpp:244-302   1 ms
+//   Acquisition::doAcqMedium   RT/objects/acquisition.cpp:309-425   10 ms coherent, 25 Hz post-correlation DFT; reads
+//                                                                   rows lcv2*20 + lcv3 (see gnssb200.h on the rows
+//                                                                   a 10-ms preparation does not fill)
 //   Acquisition::doAcqWeak     RT/objects/acquisition.cpp:433-570   10 ms coherent x 15 non-coherent, 25 Hz
 //                                                                   post-correlation DFT, code-Doppler shift,
 //                                                                   even / odd 10-ms alignment
@@ -19,6 +22,7 @@
 // the reference's loop order on the host.
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -167,7 +171,9 @@ __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, co
   if (tid == 0) out[blockIdx.x] = b;
 }
 
-// doAcqWeak: one CTA per (sv, kHz bin, 250 Hz offset, even/odd)
+// doAcqWeak: one CTA per (sv, kHz bin, 250 Hz offset, even/odd); doAcqMedium (MEDIUM): one CTA per (sv, kHz bin,
+// lcv2), a single round over rows lcv2*20 + lcv3 with the multiply shifted by 10 and no code-Doppler shift
+template <bool MEDIUM>
 __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, const uint32_t *codes, const int *sv_list, int nd, int l0,
                                                       const uint32_t *twi, unsigned rflags, const int2 *dft /* [10][10] (i, q | nq, ni) */,
                                                       Best *out) {
@@ -177,19 +183,20 @@ __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, cons
   uint32_t *scratch = sm + 20 * NS;         // [SCR]
   __shared__ Best red[NT / 32];
   __shared__ int4 dsh[100];                 // dft_rows[r][j]: i, nq, q, ni
-  const int per_sv = nd * 8, combo = blockIdx.x % per_sv, svi = blockIdx.x / per_sv;
-  const int l = l0 + combo / 8, l2 = (combo / 2) % 4, k = combo % 2, tid = threadIdx.x;
+  const int per_sv = nd * (MEDIUM ? 4 : 8), combo = blockIdx.x % per_sv, svi = blockIdx.x / per_sv;
+  const int l = l0 + combo / (MEDIUM ? 4 : 8), l2 = MEDIUM ? combo % 4 : (combo / 2) % 4, k = MEDIUM ? 0 : combo % 2, tid = threadIdx.x;
   const uint32_t *code = codes + (size_t)sv_list[svi] * NS;
   for (int j = tid; j < 100; j += NT)
     dsh[j] = make_int4((int)(int16_t)(dft[j].x & 0xffff), (int)(int16_t)((unsigned)dft[j].x >> 16), (int)(int16_t)(dft[j].y & 0xffff),
                        (int)(int16_t)((unsigned)dft[j].y >> 16));
   for (int j = tid; j < 10 * NS; j += NT) power[j] = 0;
   __syncthreads();
-  for (int i = 0; i < 15; i++) {
+  for (int i = 0; i < (MEDIUM ? 1 : 15); i++) {
     for (int l3 = 0; l3 < 10; l3++) {
-      const uint32_t *row = rows + (size_t)(l2 * 310 + l3 + i * 20 + k * 10) * ROWLEN + 100 + l;
+      const int r = MEDIUM ? l2 * 20 + l3 : l2 * 310 + l3 + i * 20 + k * 10;
+      const uint32_t *row = rows + (size_t)r * ROWLEN + 100 + l;
       uint32_t *x = coh + l3 * NS;
-      for (int j = tid; j < NS; j += NT) scratch[PAD(j)] = cmul_shift(row[j], code[j], 9);
+      for (int j = tid; j < NS; j += NT) scratch[PAD(j)] = cmul_shift(row[j], code[j], MEDIUM ? 10 : 9);
       __syncthreads();
       fft2048(scratch, x, twi, rflags);
     }
@@ -271,12 +278,18 @@ void make_dft(std::vector<int2> &d) {  // wipeoff_gen, misc.cpp:148-166; acquisi
 
 }  // namespace
 
-extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, int type, double fif, const int16_t *prn_codes, int n_codes,
-                                       const int32_t *sv_list, int n_sv, int doppmin, int doppmax, gnssb200_gpssdr_result *results) {
-  const int ms = type == 0 ? 1 : (type == 2 ? 310 : 0);
-  const int l0 = doppmin / 1000, nd = doppmax / 1000 - doppmin / 1000;
-  if (!h || !iq || !prn_codes || !sv_list || !results || ms == 0 || n_sv <= 0 || nd <= 0 || l0 < -100 || l0 + nd > 100) {
-    gnssb200_set_error(-7, "gnssb200_gpssdr_acquire: bad arguments (type 0 or 2, Doppler range within +-100 kHz)", __FILE__, __LINE__);
+static int prep_ms(int type) { return type == 0 ? 1 : (type == 1 ? 10 : (type == 2 ? 310 : 0)); }
+
+// prior_iq / prior_type: an earlier doPrepIF of the same object whose rows persist under this one (medium only)
+static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int16_t *prior_iq, int prior_type, double fif,
+                      const int16_t *prn_codes, int n_codes, const int32_t *sv_list, int n_sv, int doppmin, int doppmax,
+                      gnssb200_gpssdr_result *results) {
+  const int ms = prep_ms(type), pms = prior_iq ? prep_ms(prior_type) : 0;
+  // doAcqStrong / doAcqWeak stop before doppmax/1000, doAcqMedium includes it (acquisition.cpp:258,325,450)
+  const int l0 = doppmin / 1000, nd = doppmax / 1000 - doppmin / 1000 + (type == 1 ? 1 : 0);
+  if (!h || !iq || !prn_codes || !sv_list || !results || ms == 0 || (prior_iq && pms == 0) || n_sv <= 0 || nd <= 0 || l0 < -100 ||
+      l0 + nd - (type == 1 ? 1 : 0) > 100) {
+    gnssb200_set_error(-7, "gnssb200_gpssdr_acquire: bad arguments (type 0, 1 or 2, Doppler range within +-100 kHz)", __FILE__, __LINE__);
     return -7;
   }
   for (int i = 0; i < n_sv; i++)
@@ -291,8 +304,10 @@ extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, in
   make_wipeoff(fif, wipe);
   make_dft(dft);
   const unsigned r2flags = (1u << 7) | (1u << 9);  // R2 = {0,0,0,0,0,0,0,1,0,1,0,...}: ranks 7 and 9 of the 11 are scaled
-  const int per_sv = type == 0 ? nd * 4 : nd * 8, n_out = per_sv * n_sv;
-  uint32_t *d_iq = nullptr, *d_wipe = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_rows = nullptr, *d_codes = nullptr;
+  const int per_sv = type == 2 ? nd * 8 : nd * 4, n_out = per_sv * n_sv;
+  // rows the kernels may read: 4*ms of this preparation, 70 for doAcqMedium, those a prior preparation filled
+  const int n_rows = std::max(std::max(4 * ms, 4 * pms), type == 1 ? 70 : 0);
+  uint32_t *d_iq = nullptr, *d_piq = nullptr, *d_wipe = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_rows = nullptr, *d_codes = nullptr;
   int2 *d_dft = nullptr;
   int *d_sv = nullptr;
   Best *d_out = nullptr;
@@ -305,15 +320,18 @@ extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, in
     if (e == cudaSuccess) e = cudaMemcpy(d, s, bytes, cudaMemcpyHostToDevice);
   };
   A((void **)&d_iq, (size_t)ms * NS * 4);
+  if (pms) A((void **)&d_piq, (size_t)pms * NS * 4);
   A((void **)&d_wipe, wipe.size() * 4);
   A((void **)&d_twf, 4096);
   A((void **)&d_twi, 4096);
-  A((void **)&d_rows, (size_t)4 * ms * ROWLEN * 4);
+  A((void **)&d_rows, (size_t)n_rows * ROWLEN * 4);
   A((void **)&d_codes, (size_t)n_codes * NS * 4);
   A((void **)&d_dft, 100 * sizeof(int2));
   A((void **)&d_sv, sizeof(int) * n_sv);
   A((void **)&d_out, sizeof(Best) * n_out);
   U(d_iq, iq, (size_t)ms * NS * 4);
+  if (pms) U(d_piq, prior_iq, (size_t)pms * NS * 4);
+  if (e == cudaSuccess && type == 1) e = cudaMemset(d_rows, 0, (size_t)n_rows * ROWLEN * 4);  // a fresh object: zeroed rows
   U(d_wipe, wipe.data(), wipe.size() * 4);
   U(d_twf, twf.data(), 4096);
   U(d_twi, twi.data(), 4096);
@@ -322,20 +340,24 @@ extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, in
   U(d_sv, sv_list, sizeof(int) * n_sv);
   if (e == cudaSuccess) {
     cudaEventRecord(h->ev0, 0);
+    if (pms) gsa_prep_kernel<<<4 * pms, NT>>>(d_piq, pms, d_wipe, d_twf, d_rows);
     gsa_prep_kernel<<<4 * ms, NT>>>(d_iq, ms, d_wipe, d_twf, d_rows);
+    const size_t smem = ((size_t)20 * NS + SCR) * 4;
     if (type == 0)
       gsa_strong_kernel<<<n_out, NT>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_out);
-    else {
-      const size_t smem = ((size_t)20 * NS + SCR) * 4;
-      e = cudaFuncSetAttribute(gsa_weak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) gsa_weak_kernel<<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_dft, d_out);
+    else if (type == 1) {
+      e = cudaFuncSetAttribute(gsa_weak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) gsa_weak_kernel<true><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_dft, d_out);
+    } else {
+      e = cudaFuncSetAttribute(gsa_weak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) gsa_weak_kernel<false><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_dft, d_out);
     }
     cudaEventRecord(h->ev1, 0);
-    h->launches += 2;
+    h->launches += pms ? 3 : 2;
     if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out.data(), d_out, sizeof(Best) * n_out, cudaMemcpyDeviceToHost);
-  cudaFree(d_iq); cudaFree(d_wipe); cudaFree(d_twf); cudaFree(d_twi); cudaFree(d_rows); cudaFree(d_codes); cudaFree(d_dft); cudaFree(d_sv);
+  cudaFree(d_iq); cudaFree(d_piq); cudaFree(d_wipe); cudaFree(d_twf); cudaFree(d_twi); cudaFree(d_rows); cudaFree(d_codes); cudaFree(d_dft); cudaFree(d_sv);
   cudaFree(d_out);
   if (e != cudaSuccess) {
     gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
@@ -354,6 +376,10 @@ extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, in
           const int l = l0 + c / 4, l2 = c % 4;
           r.code_phase = 2048 - b.idx;
           r.doppler = (int32_t)((l * 1000) + (float)l2 * 250);
+        } else if (type == 1) {
+          const int l = l0 + c / 4, l2 = c % 4;
+          r.code_phase = b.idx % NS;
+          r.doppler = (int32_t)((l * 1000) + (l2 * 250) + (b.idx / NS) * 25.0);
         } else {
           const int l = l0 + c / 8, l2 = (c / 2) % 4;
           r.code_phase = b.idx % NS;
@@ -363,8 +389,23 @@ extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, in
       }
     }
     r.type = type;
-    r.success = r.magnitude > 0u ? 1 : 0;  // THRESH_STRONG = THRESH_WEAK = 0 (RT/includes/config.h:72,74)
+    r.success = r.magnitude > 0u ? 1 : 0;  // THRESH_STRONG = THRESH_MEDIUM = THRESH_WEAK = 0 (RT/includes/config.h:72-74)
     results[s] = r;
   }
   return 0;
+}
+
+extern "C" int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, int type, double fif, const int16_t *prn_codes, int n_codes,
+                                       const int32_t *sv_list, int n_sv, int doppmin, int doppmax, gnssb200_gpssdr_result *results) {
+  if (type != 0 && type != 2) {
+    gnssb200_set_error(-7, "gnssb200_gpssdr_acquire: type 0 (strong) or 2 (weak); medium is gnssb200_gpssdr_acquire_medium", __FILE__, __LINE__);
+    return -7;
+  }
+  return gpssdr_run(h, iq, type, nullptr, 0, fif, prn_codes, n_codes, sv_list, n_sv, doppmin, doppmax, results);
+}
+
+extern "C" int gnssb200_gpssdr_acquire_medium(gnssb200_handle *h, const int16_t *iq, const int16_t *prior_iq, int prior_type, double fif,
+                                              const int16_t *prn_codes, int n_codes, const int32_t *sv_list, int n_sv, int doppmin,
+                                              int doppmax, gnssb200_gpssdr_result *results) {
+  return gpssdr_run(h, iq, 1, prior_iq, prior_type, fif, prn_codes, n_codes, sv_list, n_sv, doppmin, doppmax, results);
 }

@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.gnssb200_ingest_status.argtypes = [vp, P(abi.IngestStat)]
     L.gnssb200_ingest_sync.argtypes = [vp, vp, vp]
     L.gnssb200_gpssdr_acquire.argtypes = [vp, vp, C.c_int, C.c_double, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.gnssb200_gpssdr_acquire_medium.argtypes = [vp, vp, vp, C.c_int, C.c_double, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
     L.correlator_init.argtypes = [C.c_double]
     L.Sim_GP2021_int.argtypes = [vp, C.c_long]
     if hasattr(L, "gnssb200_acq_search"):

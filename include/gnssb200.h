@@ -420,14 +420,26 @@ int gnssb200_find_time_marks(gnssb200_handle *h, const void *d_ip, int dtype, in
  * ------------------------------------------------------------------------------------------- */
 typedef struct gnssb200_gpssdr_result {
   int32_t sv;
-  int32_t type;        /* ACQ_TYPE_STRONG 0 / ACQ_TYPE_WEAK 2 */
+  int32_t type;        /* ACQ_TYPE_STRONG 0 / ACQ_TYPE_MEDIUM 1 / ACQ_TYPE_WEAK 2 */
   int32_t code_phase;  /* samples at 2.048 Msps */
   int32_t doppler;     /* Hz */
   uint32_t magnitude;
-  int32_t success;     /* magnitude > THRESH_* (both 0 in the reference, config.h:72,74) */
+  int32_t success;     /* magnitude > THRESH_* (all 0 in the reference, config.h:72-74) */
 } gnssb200_gpssdr_result;
 int gnssb200_gpssdr_acquire(gnssb200_handle *h, const int16_t *iq, int type, double fif, const int16_t *prn_codes, int n_codes,
                             const int32_t *sv_list, int n_sv, int doppmin, int doppmax, gnssb200_gpssdr_result *results);
+
+/* Acq_Command_S Acquisition::doAcqMedium(int32 sv, int32 doppmin, int32 doppmax)  RT/objects/acquisition.cpp:309,
+ * preceded by doPrepIF(ACQ_TYPE_MEDIUM, iq) with iq = 10 ms (20480 complex int16): 10 ms coherent, ten 25 Hz
+ * post-correlation DFT rows, kHz bins doppmin/1000 .. doppmax/1000 INCLUSIVE (:325), result type 1.
+ * The reference reads spectrum rows lcv2*20 + lcv3 (:340) while a 10-ms preparation fills rows offset*10 + ms
+ * (:186-234): lcv2 = 0 sees the 0 Hz rows, lcv2 = 1 the 500 Hz rows (and reports them as +250 Hz), lcv2 = 2, 3
+ * see rows 40-49 and 60-69, which keep what an EARLIER preparation of the same Acquisition object wrote.  That
+ * history is an input here: prior_iq / prior_type (0, 1 or 2; NULL = a new object whose row storage is zero)
+ * is the buffer of the last doPrepIF that ran before this one, e.g. the 310 ms of the preceding weak search. */
+int gnssb200_gpssdr_acquire_medium(gnssb200_handle *h, const int16_t *iq, const int16_t *prior_iq, int prior_type, double fif,
+                                   const int16_t *prn_codes, int n_codes, const int32_t *sv_list, int n_sv, int doppmin,
+                                   int doppmax, gnssb200_gpssdr_result *results);
 
 #ifdef __cplusplus
 }

@@ -291,3 +291,41 @@ void gso_acq_weak(GsoAcq *a, const CPX *code, int doppmin, int doppmax, GsoResul
   free(coherent);
   free(power);
 }
+
+/* doAcqMedium :309-425.  Rows lcv2*20 + lcv3 are read although a 10-ms preparation (type 1) fills rows
+ * offset*10 + ms only (:186-194,226-234): lcv2 = 0 reads the 0 Hz rows, lcv2 = 1 the 500 Hz rows (reported as
+ * +250 Hz), lcv2 = 2 and 3 read rows 40-49 and 60-69, which hold whatever an EARLIER preparation left there
+ * (this object: zeros after gso_acq_new, like a zeroed allocation; rows of the last 310-ms preparation
+ * otherwise).  The Doppler loop is inclusive (lcv <= doppmax/1000), the multiply shifts by 10. */
+void gso_acq_medium(GsoAcq *a, const CPX *code, int doppmin, int doppmax, GsoResult *res) {
+  int32_t mag = 0, magt = 0, indext = 0;
+  CPX *coherent = (CPX *)malloc(sizeof(CPX) * 10 * SAMPS_MS);
+  CPX *power = (CPX *)malloc(sizeof(CPX) * 10 * SAMPS_MS);
+  for (int l = doppmin / 1000; l <= doppmax / 1000; l++)
+    for (int l2 = 0; l2 < 4; l2++) {
+      for (int l3 = 0; l3 < 10; l3++) {
+        cmulsc(row_ptr(a, l2 * 20 + l3) + 100 + l, code, coherent + (size_t)l3 * SAMPS_MS, SAMPS_MS, 10);
+        fft_run(&a->inv, coherent + (size_t)l3 * SAMPS_MS, 1, 1);
+      }
+      for (int l3 = 0; l3 < SAMPS_MS; l3++) {
+        CPX data[10];
+        for (int j = 0; j < 10; j++) data[j] = coherent[(size_t)j * SAMPS_MS + l3];
+        for (int r = 0; r < 10; r++) {
+          int32_t ia, qa;
+          cacc(data, a->dft[r], 10, &ia, &qa);
+          power[(size_t)r * SAMPS_MS + l3].i = (int16_t)(ia >> 16);
+          power[(size_t)r * SAMPS_MS + l3].q = (int16_t)(qa >> 16);
+        }
+      }
+      cmag(power, 10 * SAMPS_MS);
+      imax((int32_t *)power, &indext, &magt, 10 * SAMPS_MS);
+      if (magt > mag) {
+        mag = magt;
+        res->code_phase = indext % SAMPS_MS;
+        res->doppler = (int32_t)((l * 1000) + (l2 * 250) + (indext / SAMPS_MS) * 25.0);
+        res->magnitude = (uint32_t)mag;
+      }
+    }
+  free(coherent);
+  free(power);
+}

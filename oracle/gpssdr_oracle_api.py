@@ -48,6 +48,7 @@ def lib():
         L.gso_prep_if.argtypes = [vp, C.c_int, vp]
         L.gso_acq_strong.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(Result)]
         L.gso_acq_weak.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(Result)]
+        L.gso_acq_medium.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(Result)]
         _lib = L
     return _lib
 
@@ -76,7 +77,7 @@ def ref():
 
 
 class GpsSdrAcquisition:
-    """Acquisition(fsample, fif) + doPrepIF + doAcqStrong / doAcqWeak of the restatement"""
+    """Acquisition(fsample, fif) + doPrepIF + doAcqStrong / doAcqMedium / doAcqWeak of the restatement"""
 
     def __init__(self, fif: float = 38400.0):
         self.L = lib()
@@ -104,3 +105,6 @@ class GpsSdrAcquisition:
 
     def doAcqWeak(self, code, doppmin, doppmax):
         return self._run(self.L.gso_acq_weak, code, doppmin, doppmax)
+
+    def doAcqMedium(self, code, doppmin, doppmax):
+        return self._run(self.L.gso_acq_medium, code, doppmin, doppmax)

@@ -67,3 +67,44 @@ def test_weak_and_strong_match_oracle():
         o.close()
     finally:
         acq.close()
+
+
+def test_medium_matches_oracle_and_committed_reference_outputs():
+    """doAcqMedium on the device: a new object (rows 40-69 zero) and after a 310-ms preparation whose rows the search reads
+    (acquisition.cpp:340), against the restatement and against the outputs of the search composed from the reference's own
+    compiled primitives (tests/golden/gpssdr_ref_golden.npz)."""
+    import os
+
+    from gnss_sdr_ru_b200 import gpssdr_codes
+    from gnss_sdr_ru_b200.gpssdr_acq import Acquisition
+    from oracle import gpssdr_oracle_api as G
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpssdr_ref_golden.npz"))
+    prior = np.random.default_rng(77).integers(-20, 21, size=(310 * 2048, 2)).astype(np.int16)
+    rec = g["medium_rec"]
+    codes = gpssdr_codes.fft_codes()
+    acq = Acquisition(fif=FIF)
+    try:
+        for tag, pr in (("fresh", None), ("prior", (2, prior))):
+            for (sv, dmin, dmax), want in zip(g["medium_cases"], g[f"medium_{tag}"]):
+                got = acq.doAcqMedium(rec, [int(sv)], int(dmin), int(dmax), prior=pr)[0]
+                assert (got["code_phase"], got["doppler"], got["magnitude"]) == tuple(int(v) for v in want), (tag, sv, got, want)
+                assert got["type"] == 1 and got["success"] == 1
+        # a wider search over several satellites in one call, random record, both histories, against the restatement
+        rng = np.random.default_rng(3)
+        rec2 = _record(rng, 10, [(6, 1.5, -1290.0, 900), (27, 1.0, 3330.0, 64)])
+        svs = [6, 27, 1, 15]
+        for pr in (None, (2, prior), (1, rec)):
+            got = acq.doAcqMedium(rec2, svs, -4000, 4000, prior=pr)
+            o = G.GpsSdrAcquisition(fif=FIF)
+            if pr is not None:
+                o.doPrepIF(pr[0], pr[1])
+            o.doPrepIF(1, rec2)
+            for sv, gg in zip(svs, got):
+                w = o.doAcqMedium(codes[sv], -4000, 4000)
+                assert (gg["code_phase"], gg["doppler"], gg["magnitude"]) == (w["code_phase"], w["doppler"], w["magnitude"]), (sv, gg, w)
+            o.close()
+        with pytest.raises(Exception):
+            acq.doAcqMedium(rec2[:100], svs, -4000, 4000)
+    finally:
+        acq.close()

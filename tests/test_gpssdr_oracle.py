@@ -162,3 +162,65 @@ def test_restated_pipeline_finds_planted_satellites():
         assert w["magnitude"] > 5 * b["magnitude"]
     finally:
         o.close()
+
+
+def _medium_inputs():
+    import hashlib
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpssdr_ref_golden.npz"))
+    prior = np.random.default_rng(77).integers(-20, 21, size=(310 * 2048, 2)).astype(np.int16)
+    assert hashlib.sha256(prior.tobytes()).digest() == g["medium_prior_sha256"].tobytes(), "numpy changed its integer stream"
+    return g, prior
+
+
+def test_medium_matches_committed_reference_outputs():
+    """doPrepIF(1) + doAcqMedium of the restatement against the same search composed from the REFERENCE's compiled
+    primitives (tests/gpssdr_refpipe.py, outputs committed by make_gpssdr_golden.py): on a new object, where rows
+    40-69 are zero, and after a 310-ms preparation, whose rows 40-69 the medium search reads (acquisition.cpp:340)."""
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    g, prior = _medium_inputs()
+    codes = gpssdr_codes.fft_codes()
+    for tag in ("fresh", "prior"):
+        o = G.GpsSdrAcquisition(fif=38400.0)
+        try:
+            if tag == "prior":
+                o.doPrepIF(2, prior)
+            o.doPrepIF(1, g["medium_rec"])
+            for (sv, dmin, dmax), want in zip(g["medium_cases"], g[f"medium_{tag}"]):
+                r = o.doAcqMedium(codes[sv], int(dmin), int(dmax))
+                assert (r["code_phase"], r["doppler"], r["magnitude"]) == tuple(int(v) for v in want), (tag, sv, r, want)
+        finally:
+            o.close()
+    # the planted satellites: sv 4 at +1040 Hz / offset 700, sv 20 at -2480 Hz / offset 1500 (index = 2048 - offset);
+    # the absent sv 9 is decided by the stale rows once they hold something
+    assert g["medium_fresh"][0][0] == 2048 - 700 and g["medium_fresh"][1][0] == 2048 - 1500 + 1
+    assert tuple(g["medium_prior"][2]) != tuple(g["medium_fresh"][2]) and g["medium_prior"][2][1] % 1000 >= 500
+
+
+@needs_ref
+def test_medium_matches_reference_composition_live():
+    """the same comparison with the reference's primitives called now (one kHz bin, both histories)"""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import gpssdr_refpipe as RP
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    _, prior = _medium_inputs()
+    codes = gpssdr_codes.fft_codes()
+    rng = np.random.default_rng(31)
+    rec = rng.integers(-30, 31, size=(10 * 2048, 2)).astype(np.int16)
+    ra = RP.RefAcquisition(RP.Prims(G.ref(), "gsr_"), n_rows=70)
+    o = G.GpsSdrAcquisition(fif=38400.0)
+    try:
+        for with_prior in (False, True):
+            if with_prior:
+                ra.prep(2, prior, max_rows=70)
+                o.doPrepIF(2, prior)
+            ra.prep(1, rec)
+            o.doPrepIF(1, rec)
+            want = RP.RefAcquisition.pick(ra.medium_cells(codes[13], -1000, -1000))
+            assert o.doAcqMedium(codes[13], -1000, -1000) == want, (with_prior, want)
+    finally:
+        o.close()

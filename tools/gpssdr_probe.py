@@ -11,4 +11,11 @@ a = Acquisition()
 for _ in range(3):
     t = time.time(); r = a.doAcqWeak(rec, list(range(32)), -10000, 10000); dt = time.time() - t
     print(f"weak 32 sv: {dt*1e3:.1f} ms wall, kernels {a.L.gnssb200_last_kernel_ms(a.h):.2f} ms")
+rec10 = rec[: 10 * 2048]
+for _ in range(3):
+    t = time.time(); r = a.doAcqMedium(rec10, list(range(32)), -10000, 10000, prior=(2, rec)); dt = time.time() - t
+    print(f"medium 32 sv (after a 310-ms preparation): {dt*1e3:.1f} ms wall, kernels {a.L.gnssb200_last_kernel_ms(a.h):.2f} ms")
+for _ in range(3):
+    t = time.time(); r = a.doAcqMedium(rec10, list(range(32)), -10000, 10000); dt = time.time() - t
+    print(f"medium 32 sv (new object): {dt*1e3:.1f} ms wall, kernels {a.L.gnssb200_last_kernel_ms(a.h):.2f} ms")
 a.close()
