@@ -108,3 +108,21 @@ def test_medium_matches_oracle_and_committed_reference_outputs():
             acq.doAcqMedium(rec2[:100], svs, -4000, 4000)
     finally:
         acq.close()
+
+
+def test_strong_and_weak_match_committed_reference_compositions():
+    """the device against the searches composed from the reference's own compiled primitives (make_gpssdr_golden.py)"""
+    from gnss_sdr_ru_b200.gpssdr_acq import Acquisition
+    from test_gpssdr_oracle import composed_records
+
+    g, wrec, srec = composed_records()
+    acq = Acquisition(fif=FIF)
+    try:
+        for (sv, dmin, dmax), want in zip(g["strong_cases"], g["strong_ref"]):
+            r = acq.doAcqStrong(srec, [int(sv)], int(dmin), int(dmax))[0]
+            assert (r["code_phase"], r["doppler"], r["magnitude"]) == tuple(int(v) for v in want), (sv, r, want)
+        for (sv, dmin, dmax), want in zip(g["weak_cases"], g["weak_ref"]):
+            r = acq.doAcqWeak(wrec, [int(sv)], int(dmin), int(dmax))[0]
+            assert (r["code_phase"], r["doppler"], r["magnitude"]) == tuple(int(v) for v in want), (sv, r, want)
+    finally:
+        acq.close()

@@ -224,3 +224,67 @@ def test_medium_matches_reference_composition_live():
             assert o.doAcqMedium(codes[13], -1000, -1000) == want, (with_prior, want)
     finally:
         o.close()
+
+
+WEAK_REC = dict(seed=11, ms=310, sats=[(4, 1, 1480, 700)], noise=12)
+STRONG_REC = dict(seed=12, ms=1, sats=[(7, 4, -2300, 300), (22, 3, 3900, 1777)], noise=12)
+
+
+def composed_records():
+    """the integer-only records of make_gpssdr_golden.py, checked against the hashes it stored"""
+    import hashlib
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import gpssdr_refpipe as RP
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpssdr_ref_golden.npz"))
+    wrec, srec = RP.int_record(**WEAK_REC), RP.int_record(**STRONG_REC)
+    assert hashlib.sha256(wrec.tobytes()).digest() == g["weak_rec_sha256"].tobytes()
+    assert hashlib.sha256(srec.tobytes()).digest() == g["strong_rec_sha256"].tobytes()
+    return g, wrec, srec
+
+
+def test_strong_and_weak_match_committed_reference_compositions():
+    """doPrepIF + doAcqStrong / doAcqWeak of the restatement against the same searches composed from the REFERENCE's
+    compiled primitives (every (kHz bin, offset, alignment) cell through gsr_cmulsc / gsr_fft / gsr_cacc / gsr_cmag /
+    gsr_max; outputs committed by make_gpssdr_golden.py)"""
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    g, wrec, srec = composed_records()
+    codes = gpssdr_codes.fft_codes()
+    o = G.GpsSdrAcquisition(fif=38400.0)
+    try:
+        o.doPrepIF(0, srec)
+        for (sv, dmin, dmax), want in zip(g["strong_cases"], g["strong_ref"]):
+            r = o.doAcqStrong(codes[sv], int(dmin), int(dmax))
+            assert (r["code_phase"], r["doppler"], r["magnitude"]) == tuple(int(v) for v in want), (sv, r, want)
+        o.doPrepIF(2, wrec)
+        for (sv, dmin, dmax), want in zip(g["weak_cases"], g["weak_ref"]):
+            r = o.doAcqWeak(codes[sv], int(dmin), int(dmax))
+            assert (r["code_phase"], r["doppler"], r["magnitude"]) == tuple(int(v) for v in want), (sv, r, want)
+    finally:
+        o.close()
+    assert abs(int(g["strong_ref"][0][0]) - 300) <= 1 and abs(int(g["strong_ref"][1][0]) - 1777) <= 1
+    assert int(g["weak_ref"][0][2]) > 10 * int(g["weak_ref"][1][2])
+
+
+@needs_ref
+def test_strong_matches_reference_composition_live():
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import gpssdr_refpipe as RP
+    from gnss_sdr_ru_b200 import gpssdr_codes
+
+    codes = gpssdr_codes.fft_codes()
+    rec = RP.int_record(99, 1, [(15, 5, 640, 1234)], noise=700)  # large noise: the unscaled forward FFT wraps in int16
+    ra = RP.RefAcquisition(RP.Prims(G.ref(), "gsr_"), n_rows=4)
+    ra.prep(0, rec)
+    o = G.GpsSdrAcquisition(fif=38400.0)
+    try:
+        o.doPrepIF(0, rec)
+        for sv in (15, 2):
+            assert o.doAcqStrong(codes[sv], -3000, 3000) == RP.RefAcquisition.pick_strong(ra.strong_cells(codes[sv], -3000, 3000))
+    finally:
+        o.close()
