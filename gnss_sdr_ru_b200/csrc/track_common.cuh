@@ -59,13 +59,17 @@ __device__ __forceinline__ int sext8(uint32_t w, int k) {
 // 8-phase LO of the GP2021 / Namuru carrier NCO (correlator.c:203-204, NAM/rtl/carrier_nco.v:21-25),
 // stored so that  I*lut.x + Q*lut.y = ival + 65536*qval  with
 //   ival = i_lo*I + q_lo*Q,  qval = q_lo*I - i_lo*Q   (correlator.c:214-215)
+// The small tables below are nibbles of a literal (entry k = sign-extended nibble k): a `const int t[8]` indexed at run
+// time is a stack array, i.e. local-memory stores and loads in every thread's prologue.
+__device__ __forceinline__ int nib(uint32_t packed, int k) { return (int)(packed << (28 - 4 * k)) >> 28; }
+__device__ __forceinline__ int lo_i(int k) { return nib(0xEEF1221Fu, k); }  // {-1, 1, 2, 2, 1, -1, -2, -2}
+__device__ __forceinline__ int lo_q(int k) { return nib(0x1FEEF122u, k); }  // {2, 2, 1, -1, -2, -2, -1, 1}
+__device__ __forceinline__ int sample_val(uint32_t code) { return nib(0xD3F1u, (int)(code & 3u)); }  // {1, -1, 3, -3}, win32_sampler.h:45-55
 __device__ __forceinline__ void fill_lo_lut(uint2 *lut) {
-  const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
-  const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
   if (threadIdx.x < 8) {
     int k = threadIdx.x;
-    lut[k].x = (uint32_t)(i_lo[k] + 65536 * q_lo[k]);
-    lut[k].y = (uint32_t)(q_lo[k] - 65536 * i_lo[k]);
+    lut[k].x = (uint32_t)(lo_i(k) + 65536 * lo_q(k));
+    lut[k].y = (uint32_t)(lo_q(k) - 65536 * lo_i(k));
   }
 }
 
@@ -81,9 +85,8 @@ __device__ __forceinline__ void load_sample(const uint8_t *blk, int fmt, int i, 
     Q = p[1];
   } else if (fmt == GNSSB200_FMT_PACKED2) {
     uint32_t b = blk[i >> 1] >> ((i & 1) * 4);
-    const int val[4] = {1, -1, 3, -3};  // FE/.../win32_sampler.h:45-55
-    I = val[b & 3];
-    Q = val[(b >> 2) & 3];
+    I = sample_val(b);  // FE/.../win32_sampler.h:45-55
+    Q = sample_val(b >> 2);
   } else {
     I = ((const int8_t *)blk)[i];
     Q = 0;
@@ -453,8 +456,6 @@ __device__ __forceinline__ void finalize_fast(ChanShared &cs, const StepParams &
 // literal per-sample walk of one block by a single lane (any register contents)
 __device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, const uint32_t *code_table, int fmt, int nsamp,
                                           const uint8_t *blk) {
-  const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
-  const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
   gnssb200_corr &g = cs.g;
   ChRegs &r = cs.r;
   const long long row = (long long)r.w_prn * HALF_CHIPS;
@@ -471,8 +472,8 @@ __device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, 
     const int k = g.carrier_phase >> 29;
     int I, Q;
     load_sample(blk, fmt, i, I, Q);
-    const int vq = q_lo[k] * I - i_lo[k] * Q;
-    const int vi = i_lo[k] * I + q_lo[k] * Q;
+    const int vq = lo_q(k) * I - lo_i(k) * Q;
+    const int vi = lo_i(k) * I + lo_q(k) * Q;
     g.acc[0] += cL * vi;
     g.acc[1] += cL * vq;
     g.acc[2] += cP * vi;

@@ -37,13 +37,10 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
     tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   if (packed_native) {
-    const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
-    const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
-    const int val[4] = {1, -1, 3, -3};
     for (int i = tid; i < 128 * 32; i += blockDim.x) {
       const int e = i >> 5, ph = e >> 4, code = e & 15;
-      const int I = val[code & 3], Q = val[code >> 2];
-      const int ival = i_lo[ph] * I + q_lo[ph] * Q, qval = q_lo[ph] * I - i_lo[ph] * Q;  // correlator.c:214-215
+      const int I = sample_val((uint32_t)code), Q = sample_val((uint32_t)code >> 2);
+      const int ival = lo_i(ph) * I + lo_q(ph) * Q, qval = lo_q(ph) * I - lo_i(ph) * Q;  // correlator.c:214-215
       vlut[i] = (uint32_t)(ival + 65536 * qval);
     }
   }
@@ -52,10 +49,9 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
     alias_tbl[tid] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   for (int i = tid; i < 256; i += blockDim.x) {
-    const int val[4] = {1, -1, 3, -3};
     uint32_t wv = 0;
 #pragma unroll
-    for (int e = 0; e < 4; e++) wv |= (uint32_t)(val[(i >> (2 * e)) & 3] & 0xff) << (8 * e);
+    for (int e = 0; e < 4; e++) wv |= (uint32_t)(sample_val((uint32_t)i >> (2 * e)) & 0xff) << (8 * e);
     unpack_lut[i] = wv;
   }
   const size_t blk_bytes = bytes_for(fmt, a.nsamp);
@@ -332,8 +328,10 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
         cs.g.carrier_cycle += sp.cyc_pending;
         if (sp.mode == MODE_FAST)
           finalize_fast(cs, sp, A, B, a.nsamp);
-        else if (sp.mode == MODE_SERIAL)
-          serial_block(cs, sp, a.code_table, fmt, a.nsamp, use_tma ? tile : blk);
+        else if (sp.mode == MODE_SERIAL) {
+          const StepParams p_tmp = sp;  // a copy: `sp` itself must not have its address taken (see track_ws.cuh)
+          serial_block(cs, p_tmp, a.code_table, fmt, a.nsamp, use_tma ? tile : blk);
+        }
         else
           cs.dumped_last = 0;
 #ifdef TRACK_PROFILE

@@ -136,13 +136,10 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   // channel-independent tables first: they fill while the control lane may still be waiting for its item
   fill_lo_lut(lut);
   if (packed_native) {
-    const int i_lo[8] = {-1, 1, 2, 2, 1, -1, -2, -2};
-    const int q_lo[8] = {2, 2, 1, -1, -2, -2, -1, 1};
-    const int val[4] = {1, -1, 3, -3};
     for (int i = tid; i < 128 * 32; i += WS_THREADS) {
       const int e = i >> 5, ph = e >> 4, code = e & 15;
-      const int I = val[code & 3], Q = val[code >> 2];
-      const int ival = i_lo[ph] * I + q_lo[ph] * Q, qval = q_lo[ph] * I - i_lo[ph] * Q;  // correlator.c:214-215
+      const int I = sample_val((uint32_t)code), Q = sample_val((uint32_t)code >> 2);
+      const int ival = lo_i(ph) * I + lo_q(ph) * Q, qval = lo_q(ph) * I - lo_i(ph) * Q;  // correlator.c:214-215
       vlut[i] = (uint32_t)(ival + 65536 * qval);
     }
   }
@@ -301,7 +298,11 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
         CP(c_acc)
       } else if (was_mode == MODE_SERIAL) {
         mbar_wait(&dfull[slot], (uint32_t)((b >> 1) & 1));
-        serial_block(cs, sp, a.code_table, fmt, a.nsamp, tiles + (size_t)slot * tile_bytes);
+        {  // a copy: only it has its address taken, so the loop's own block parameters stay in registers (with `sp`
+           // itself passed, every update of it in this loop is also stored to the stack: ~36 local stores per block)
+          const StepParams p_tmp = sp;
+          serial_block(cs, p_tmp, a.code_table, fmt, a.nsamp, tiles + (size_t)slot * tile_bytes);
+        }
         if (!last) prepare_block_state(cs, sp, a);
       } else
         cs.dumped_last = 0;
