@@ -56,24 +56,20 @@ __device__ __forceinline__ uint32_t cmul_shift(uint32_t a, uint32_t b, int shift
 // butterflies (bfly / bfly_noscale :401-440).  in: the 2048 packed CPX in natural order, PADDED by one word per 32
 // (element j at in[PAD(j)]) so that the bit-reversed gather below -- 32 consecutive targets differ only in the
 // high source-address bits -- does not land a whole warp on one bank.  x: result, natural order.  tw: the 1024
-// twiddles (i, q) of W or iW.  rflags bit r = scale rank r by >>1 first.  All NT threads of the CTA.
-// Ranks 0-4 only combine elements inside aligned groups of 32: they run in registers, one element per lane, with
-// one warp shuffle per rank; ranks 5-10 go through shared memory (bank-conflict free from there on).
+// twiddles (i, q) of W or iW.  RF bit r = scale rank r by >>1 first (a compile-time pattern: R1 = none for the
+// forward transform, R2 = ranks 7 and 9 for the inverse one).  All NT threads of the CTA.
+// Ranks 0-4 only combine elements inside aligned groups of 32: they run in registers, one element per lane; the
+// upper lane of a pair forms the product B*W, the lower lane keeps A, one shuffle swaps the two.  Ranks 5-10 go
+// through shared memory (bank-conflict free from there on).
+// Arithmetic note: the reference stores the rounded product in an int16 before adding it to A; A +- product is
+// stored as int16 again, so only the low 16 bits of the sum matter and the intermediate truncation can be skipped
+// wherever the product stays in a 32-bit register.
 #define PAD(j) ((j) + ((j) >> 5))
-__device__ __forceinline__ uint32_t bfly_half(uint32_t mine, uint32_t other, bool upper, uint32_t w, bool scale) {
-  // this lane holds A (lower, !upper) or B (upper) of a butterfly; `other` is the partner's element
-  Cpx16 A = unpack16(upper ? other : mine), B = unpack16(upper ? mine : other);
-  const Cpx16 W = unpack16(w);
-  if (scale) {
-    A.i >>= 1; A.q >>= 1; B.i >>= 1; B.q >>= 1;
-  }
-  int bi = (int)B.i * W.i - (int)B.q * W.q, bq = (int)B.i * W.q + (int)B.q * W.i;
-  bi = (bi + 8192) >> 14;
-  bq = (bq + 8192) >> 14;
-  const int16_t sbi = (int16_t)bi, sbq = (int16_t)bq;
-  return upper ? pack16((int16_t)(A.i - sbi), (int16_t)(A.q - sbq)) : pack16((int16_t)(A.i + sbi), (int16_t)(A.q + sbq));
-}
-__device__ void fft2048(const uint32_t *in, uint32_t *x, const uint32_t *__restrict__ tw, unsigned rflags) {
+constexpr unsigned RF_NONE = 0u, RF_R2 = (1u << 7) | (1u << 9);  // R1 / R2 of acquisition.cpp:75-76
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
+template <unsigned RF>
+__device__ void fft2048(const uint32_t *in, uint32_t *x, const uint32_t *__restrict__ tw) {
   const int tid = threadIdx.x, lane = tid & 31;
   for (int l = tid; l < NS; l += NT) {  // a warp owns the aligned group of 32 around l
     const int src = (int)(__brev((unsigned)l) >> 21);
@@ -81,30 +77,38 @@ __device__ void fft2048(const uint32_t *in, uint32_t *x, const uint32_t *__restr
 #pragma unroll
     for (int r = 0; r < 5; r++) {
       const int bsize = 1 << r;
-      const uint32_t other = __shfl_xor_sync(0xffffffffu, v, bsize);
+      const bool upper = (lane >> r) & 1;
       const uint32_t w = __ldg(tw + ((lane & (bsize - 1)) << (10 - r)));
-      v = bfly_half(v, other, (lane >> r) & 1, w, (rflags >> r) & 1);
+      int vi = lo16(v), vq = hi16(v);
+      if ((RF >> r) & 1) {
+        vi >>= 1;
+        vq >>= 1;
+      }
+      const int wi = lo16(w), wq = hi16(w);
+      const int pi = (vi * wi + 8192 - vq * wq) >> 14, pq = (vi * wq + 8192 + vq * wi) >> 14;  // used by the upper lanes
+      const uint32_t got = __shfl_xor_sync(0xffffffffu, upper ? pack16(pi, pq) : pack16(vi, vq), bsize);
+      const int gi = lo16(got), gq = hi16(got);
+      // lower lane: A + P with A its own element and P received; upper lane: A - P with A received and P its own
+      v = pack16(gi + (upper ? -pi : vi), gq + (upper ? -pq : vq));
     }
     x[l] = v;
   }
   __syncthreads();
+#pragma unroll
   for (int r = 5; r < 11; r++) {
     const int bsize = 1 << r, nblocks = 1024 >> r;
-    const bool scale = (rflags >> r) & 1;
     for (int t = tid; t < 1024; t += NT) {
       const int blk = t >> r, j = t & (bsize - 1);
       const int ia = (blk << (r + 1)) + j, ib = ia + bsize;
-      Cpx16 A = unpack16(x[ia]), B = unpack16(x[ib]);
-      const Cpx16 W = unpack16(__ldg(tw + j * nblocks));
-      if (scale) {
-        A.i >>= 1; A.q >>= 1; B.i >>= 1; B.q >>= 1;
+      const uint32_t a = x[ia], b = x[ib], w = __ldg(tw + j * nblocks);
+      int ai = lo16(a), aq = hi16(a), bi = lo16(b), bq = hi16(b);
+      if ((RF >> r) & 1) {
+        ai >>= 1; aq >>= 1; bi >>= 1; bq >>= 1;
       }
-      int bi = (int)B.i * W.i - (int)B.q * W.q, bq = (int)B.i * W.q + (int)B.q * W.i;
-      bi = (bi + 8192) >> 14;
-      bq = (bq + 8192) >> 14;
-      const int16_t sbi = (int16_t)bi, sbq = (int16_t)bq;
-      x[ib] = pack16((int16_t)(A.i - sbi), (int16_t)(A.q - sbq));
-      x[ia] = pack16((int16_t)(A.i + sbi), (int16_t)(A.q + sbq));
+      const int wi = lo16(w), wq = hi16(w);
+      const int pi = (bi * wi + 8192 - bq * wq) >> 14, pq = (bi * wq + 8192 + bq * wi) >> 14;
+      x[ib] = pack16(ai - pi, aq - pq);
+      x[ia] = pack16(ai + pi, aq + pq);
     }
     __syncthreads();
   }
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(NT) gsa_prep_kernel(const uint32_t *iq, int ms
   for (int j = tid; j < NS; j += NT)
     scratch[PAD(j)] = cmul_shift(iq[(size_t)m * NS + j], wipe[(size_t)off * 10 * NS + (m % 10) * NS + j], 14);
   __syncthreads();
-  fft2048(scratch, x, twf, 0u);  // R1: no rank is scaled
+  fft2048<RF_NONE>(scratch, x, twf);  // R1: no rank is scaled
   uint32_t *p = rows + (size_t)row * ROWLEN;
   for (int j = tid; j < ROWLEN - 1; j += NT) p[j] = x[(j + NS - 100) & (NS - 1)];  // 100 wrapped bins on either side
   if (tid == 0) p[ROWLEN - 1] = 0;
@@ -148,7 +152,7 @@ __device__ Best block_first_max(int mag, int idx, Best *red) {
 
 // doAcqStrong: one CTA per (sv, kHz bin, 250 Hz offset)
 __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, const uint32_t *codes, const int *sv_list, int nd, int l0,
-                                                        const uint32_t *twi, unsigned rflags, Best *out) {
+                                                        const uint32_t *twi, Best *out) {
   __shared__ uint32_t x[NS], scratch[SCR];
   __shared__ Best red[NT / 32];
   const int combo = blockIdx.x % (nd * 4), svi = blockIdx.x / (nd * 4);
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, co
   const uint32_t *row = rows + (size_t)l2 * ROWLEN + 100 + l;
   for (int j = tid; j < NS; j += NT) scratch[PAD(j)] = cmul_shift(row[j], code[j], 10);
   __syncthreads();
-  fft2048(scratch, x, twi, rflags);
+  fft2048<RF_R2>(scratch, x, twi);
   int mag = 0, idx = 0;
   for (int j = tid; j < NS; j += NT) {
     const Cpx16 c = unpack16(x[j]);
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, co
 // lcv2), a single round over rows lcv2*20 + lcv3 with the multiply shifted by 10 and no code-Doppler shift
 template <bool MEDIUM>
 __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, const uint32_t *codes, const int *sv_list, int nd, int l0,
-                                                      const uint32_t *twi, unsigned rflags, const int2 *dft /* [10][10] (i, q | nq, ni) */,
+                                                      const uint32_t *twi, const int2 *dft /* [10][10] (i, q | nq, ni) */,
                                                       Best *out) {
   extern __shared__ uint32_t sm[];
   uint32_t *coh = sm;                       // [10][2048] packed CPX
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, cons
       uint32_t *x = coh + l3 * NS;
       for (int j = tid; j < NS; j += NT) scratch[PAD(j)] = cmul_shift(row[j], code[j], MEDIUM ? 10 : 9);
       __syncthreads();
-      fft2048(scratch, x, twi, rflags);
+      fft2048<RF_R2>(scratch, x, twi);
     }
     // code-Doppler shift of this round (acquisition.cpp:486-492)
     const double doppler = (double)(l * 1000) + (float)(l2 * 250);
@@ -303,7 +307,6 @@ static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int
   make_twiddles(twf, twi);
   make_wipeoff(fif, wipe);
   make_dft(dft);
-  const unsigned r2flags = (1u << 7) | (1u << 9);  // R2 = {0,0,0,0,0,0,0,1,0,1,0,...}: ranks 7 and 9 of the 11 are scaled
   const int per_sv = type == 2 ? nd * 8 : nd * 4, n_out = per_sv * n_sv;
   // rows the kernels may read: 4*ms of this preparation, 70 for doAcqMedium, those a prior preparation filled
   const int n_rows = std::max(std::max(4 * ms, 4 * pms), type == 1 ? 70 : 0);
@@ -344,13 +347,13 @@ static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int
     gsa_prep_kernel<<<4 * ms, NT>>>(d_iq, ms, d_wipe, d_twf, d_rows);
     const size_t smem = ((size_t)20 * NS + SCR) * 4;
     if (type == 0)
-      gsa_strong_kernel<<<n_out, NT>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_out);
+      gsa_strong_kernel<<<n_out, NT>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_out);
     else if (type == 1) {
       e = cudaFuncSetAttribute(gsa_weak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) gsa_weak_kernel<true><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_dft, d_out);
+      if (e == cudaSuccess) gsa_weak_kernel<true><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_dft, d_out);
     } else {
       e = cudaFuncSetAttribute(gsa_weak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) gsa_weak_kernel<false><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, r2flags, d_dft, d_out);
+      if (e == cudaSuccess) gsa_weak_kernel<false><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_dft, d_out);
     }
     cudaEventRecord(h->ev1, 0);
     h->launches += pms ? 3 : 2;
