@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(NT) gsa_prep_kernel(const uint32_t *iq, int ms
   if (tid == 0) p[ROWLEN - 1] = 0;
 }
 
+// dft_rows[r][j] of the post-correlation DFT as (i, nq, q, ni): constant-bank operands of the multiply-adds
+__constant__ int4 c_dft[100];
+
 struct Best {
   int mag, idx;
 };
@@ -179,20 +182,15 @@ __global__ void __launch_bounds__(NT) gsa_strong_kernel(const uint32_t *rows, co
 // lcv2), a single round over rows lcv2*20 + lcv3 with the multiply shifted by 10 and no code-Doppler shift
 template <bool MEDIUM>
 __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, const uint32_t *codes, const int *sv_list, int nd, int l0,
-                                                      const uint32_t *twi, const int2 *dft /* [10][10] (i, q | nq, ni) */,
-                                                      Best *out) {
+                                                      const uint32_t *twi, Best *out) {
   extern __shared__ uint32_t sm[];
   uint32_t *coh = sm;                       // [10][2048] packed CPX
   int *power = (int *)(sm + 10 * NS);       // [10][2048]
   uint32_t *scratch = sm + 20 * NS;         // [SCR]
   __shared__ Best red[NT / 32];
-  __shared__ int4 dsh[100];                 // dft_rows[r][j]: i, nq, q, ni
   const int per_sv = nd * (MEDIUM ? 4 : 8), combo = blockIdx.x % per_sv, svi = blockIdx.x / per_sv;
   const int l = l0 + combo / (MEDIUM ? 4 : 8), l2 = MEDIUM ? combo % 4 : (combo / 2) % 4, k = MEDIUM ? 0 : combo % 2, tid = threadIdx.x;
   const uint32_t *code = codes + (size_t)sv_list[svi] * NS;
-  for (int j = tid; j < 100; j += NT)
-    dsh[j] = make_int4((int)(int16_t)(dft[j].x & 0xffff), (int)(int16_t)((unsigned)dft[j].x >> 16), (int)(int16_t)(dft[j].y & 0xffff),
-                       (int)(int16_t)((unsigned)dft[j].y >> 16));
   for (int j = tid; j < 10 * NS; j += NT) power[j] = 0;
   __syncthreads();
   for (int i = 0; i < (MEDIUM ? 1 : 15); i++) {
@@ -217,11 +215,12 @@ __global__ void __launch_bounds__(NT) gsa_weak_kernel(const uint32_t *rows, cons
         dq[j] = c.q;
       }
       const int col = (d + shift + NS) % NS;
+#pragma unroll
       for (int r = 0; r < 10; r++) {
         int ia = 0, qa = 0;  // x86_cacc :220-251
 #pragma unroll
         for (int j = 0; j < 10; j++) {
-          const int4 w = dsh[r * 10 + j];
+          const int4 w = c_dft[r * 10 + j];
           ia += di[j] * w.x + dq[j] * w.y;
           qa += di[j] * w.z + dq[j] * w.w;
         }
@@ -311,7 +310,6 @@ static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int
   // rows the kernels may read: 4*ms of this preparation, 70 for doAcqMedium, those a prior preparation filled
   const int n_rows = std::max(std::max(4 * ms, 4 * pms), type == 1 ? 70 : 0);
   uint32_t *d_iq = nullptr, *d_piq = nullptr, *d_wipe = nullptr, *d_twf = nullptr, *d_twi = nullptr, *d_rows = nullptr, *d_codes = nullptr;
-  int2 *d_dft = nullptr;
   int *d_sv = nullptr;
   Best *d_out = nullptr;
   std::vector<Best> out(n_out);
@@ -329,7 +327,6 @@ static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int
   A((void **)&d_twi, 4096);
   A((void **)&d_rows, (size_t)n_rows * ROWLEN * 4);
   A((void **)&d_codes, (size_t)n_codes * NS * 4);
-  A((void **)&d_dft, 100 * sizeof(int2));
   A((void **)&d_sv, sizeof(int) * n_sv);
   A((void **)&d_out, sizeof(Best) * n_out);
   U(d_iq, iq, (size_t)ms * NS * 4);
@@ -339,7 +336,12 @@ static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int
   U(d_twf, twf.data(), 4096);
   U(d_twi, twi.data(), 4096);
   U(d_codes, prn_codes, (size_t)n_codes * NS * 4);
-  U(d_dft, dft.data(), 100 * sizeof(int2));
+  if (e == cudaSuccess) {
+    int4 d4[100];
+    for (int k = 0; k < 100; k++)
+      d4[k] = make_int4((int16_t)(dft[k].x & 0xffff), (int16_t)((unsigned)dft[k].x >> 16), (int16_t)(dft[k].y & 0xffff), (int16_t)((unsigned)dft[k].y >> 16));
+    e = cudaMemcpyToSymbol(c_dft, d4, sizeof d4);
+  }
   U(d_sv, sv_list, sizeof(int) * n_sv);
   if (e == cudaSuccess) {
     cudaEventRecord(h->ev0, 0);
@@ -350,17 +352,17 @@ static int gpssdr_run(gnssb200_handle *h, const int16_t *iq, int type, const int
       gsa_strong_kernel<<<n_out, NT>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_out);
     else if (type == 1) {
       e = cudaFuncSetAttribute(gsa_weak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) gsa_weak_kernel<true><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_dft, d_out);
+      if (e == cudaSuccess) gsa_weak_kernel<true><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_out);
     } else {
       e = cudaFuncSetAttribute(gsa_weak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess) gsa_weak_kernel<false><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_dft, d_out);
+      if (e == cudaSuccess) gsa_weak_kernel<false><<<n_out, NT, smem>>>(d_rows, d_codes, d_sv, nd, l0, d_twi, d_out);
     }
     cudaEventRecord(h->ev1, 0);
     h->launches += pms ? 3 : 2;
     if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out.data(), d_out, sizeof(Best) * n_out, cudaMemcpyDeviceToHost);
-  cudaFree(d_iq); cudaFree(d_piq); cudaFree(d_wipe); cudaFree(d_twf); cudaFree(d_twi); cudaFree(d_rows); cudaFree(d_codes); cudaFree(d_dft); cudaFree(d_sv);
+  cudaFree(d_iq); cudaFree(d_piq); cudaFree(d_wipe); cudaFree(d_twf); cudaFree(d_twi); cudaFree(d_rows); cudaFree(d_codes); cudaFree(d_sv);
   cudaFree(d_out);
   if (e != cudaSuccess) {
     gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
