@@ -326,9 +326,16 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
   CUDA_TRY(cudaSetDevice(h->device));
   const int S = h->n_streams;
   const size_t blk_bytes = fmt_bytes(fmt, nsamp);
-  // Two staging buffers of about 1024 blocks per stream each (>= 32 MiB, <= 512 MiB): long enough that the
-  // per-launch prologue of the channel kernel (code-table row, state load / store) stays negligible.
-  size_t stage_target = blk_bytes * (size_t)S * 1024;
+  // Two staging buffers of about 384 blocks per stream each (>= 32 MiB, <= 512 MiB): long enough that the
+  // per-launch prologue of the channel kernel (code-table row, state load / store) stays negligible, short enough
+  // that the first copy and the last kernel, which overlap with nothing, stay small (64 streams x 10 s, copy bound:
+  // 1.172 M channel*Msamples/s end to end with 1024 blocks, 1.197 M with 512, 1.203 M with 384).
+  static long long stage_blocks = 0;  // GNSSB200_STAGE_BLOCKS overrides the chunk length (blocks per stream)
+  if (!stage_blocks) {
+    const char *e = getenv("GNSSB200_STAGE_BLOCKS");
+    stage_blocks = (e && atoll(e) > 0) ? atoll(e) : 384;
+  }
+  size_t stage_target = blk_bytes * (size_t)S * (size_t)stage_blocks;
   if (stage_target < ((size_t)32 << 20)) stage_target = (size_t)32 << 20;
   if (stage_target > ((size_t)512 << 20)) stage_target = (size_t)512 << 20;
   long long chunk = (long long)(stage_target / (blk_bytes * (size_t)S));
