@@ -154,6 +154,8 @@ extern "C" void gnssb200_close(gnssb200_handle *h) {
   cudaFree(h->stage_dumps);
   cudaFree(h->stage_cnt);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_back) cudaStreamDestroy(h->s_back);
+  if (h->h_snap) cudaFreeHost(h->h_snap);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -279,6 +281,14 @@ extern "C" int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks) {
   return 0;
 }
 
+extern "C" int gnssb200_set_stage_blocks(gnssb200_handle *h, int64_t blocks) {
+  if (!h || blocks < 0) return -1;
+  h->stage_blocks = blocks;
+  return 0;
+}
+
+extern "C" int64_t gnssb200_readback_fallbacks(const gnssb200_handle *h) { return h ? h->back_fallbacks : -1; }
+
 extern "C" int64_t gnssb200_launch_count(const gnssb200_handle *h) { return h->launches; }
 
 extern "C" float gnssb200_last_kernel_ms(gnssb200_handle *h) {
@@ -313,6 +323,14 @@ extern "C" int gnssb200_track_run(gnssb200_handle *h, const void *d_if, size_t s
 // Host-buffer variant.  The record is streamed through two device staging buffers in chunks of
 // blocks: the H2D copy of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream);
 // receiver state stays on the device between chunks.  Pass pinned host memory for full PCIe speed.
+// Dump records go back while the run is still in progress (third stream, the other PCIe direction): after every
+// chunk the window of record indices that chunk can have written -- one record per code period, so indices
+// [count before, count after) sit around first_block * nsamp / samp_rate * 1000 -- is copied for all channels at
+// once (2-D copy), margins of 16 records either side.  The exact counts after every chunk come back too; the
+// host checks afterwards that every chunk's records lay inside that chunk's window and otherwise repeats the
+// read-back in one piece (channels resumed at very different counts, a receiver whose code period is not 1 ms).
+// Host buffers that are not pinned take the one-piece path from the start (an "async" copy to pageable memory
+// would block the loop that feeds the pipeline).
 extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stride, int fmt, int nsamp, int64_t nblocks,
                                        gnssb200_dump *h_dumps, int dump_cap, int32_t *h_dump_count) {
   if (!h || h->n_streams <= 0) {
@@ -330,16 +348,17 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
   // per-launch prologue of the channel kernel (code-table row, state load / store) stays negligible, short enough
   // that the first copy and the last kernel, which overlap with nothing, stay small (64 streams x 10 s, copy bound:
   // 1.172 M channel*Msamples/s end to end with 1024 blocks, 1.197 M with 512, 1.203 M with 384).
-  static long long stage_blocks = 0;  // GNSSB200_STAGE_BLOCKS overrides the chunk length (blocks per stream)
-  if (!stage_blocks) {
+  static long long env_blocks = -1;  // GNSSB200_STAGE_BLOCKS overrides the chunk length (blocks per stream)
+  if (env_blocks < 0) {
     const char *e = getenv("GNSSB200_STAGE_BLOCKS");
-    stage_blocks = (e && atoll(e) > 0) ? atoll(e) : 384;
+    env_blocks = (e && atoll(e) > 0) ? atoll(e) : 0;
   }
-  size_t stage_target = blk_bytes * (size_t)S * (size_t)stage_blocks;
+  size_t stage_target = blk_bytes * (size_t)S * (size_t)(env_blocks ? env_blocks : 384);
   if (stage_target < ((size_t)32 << 20)) stage_target = (size_t)32 << 20;
   if (stage_target > ((size_t)512 << 20)) stage_target = (size_t)512 << 20;
   long long chunk = (long long)(stage_target / (blk_bytes * (size_t)S));
-  if (chunk < 16) chunk = 16;
+  if (h->stage_blocks > 0) chunk = h->stage_blocks;  // exact, for tests of the chunked pipeline
+  else if (chunk < 16) chunk = 16;
   if (chunk > nblocks) chunk = nblocks;
   const size_t dstride = (blk_bytes * (size_t)chunk + 255) & ~(size_t)255;
   int rc = 0;
@@ -355,6 +374,7 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
   if (!h->s_copy) {
     TRY_(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     TRY_(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    TRY_(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
       TRY_(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
       TRY_(cudaEventCreateWithFlags(&h->ev_used[i], cudaEventDisableTiming));
@@ -395,6 +415,44 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
     else
       TRY_(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * S * NCH, s_comp));
   }
+  // windowed read-back of the dump records: only into pinned host memory
+  const long long nchunks = nblocks > 0 ? (nblocks + chunk - 1) / chunk : 0;
+  const int NR = S * NCH;
+  bool windows = want && !rc && nchunks > 1;
+  if (windows) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, h_dumps) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      windows = false;
+    }
+  }
+  if (windows && sizeof(int32_t) * NR * (size_t)nchunks > h->h_snap_cap) {
+    if (h->h_snap) cudaFreeHost(h->h_snap);
+    h->h_snap = nullptr;
+    TRY_(cudaHostAlloc((void **)&h->h_snap, sizeof(int32_t) * NR * (size_t)nchunks, cudaHostAllocDefault));
+    h->h_snap_cap = rc ? 0 : sizeof(int32_t) * NR * (size_t)nchunks;
+  }
+  long long cnt0_min = 0, cnt0_max = 0;  // counts the run starts from (host memory, readable now)
+  if (windows && h_dump_count) {
+    cnt0_min = cnt0_max = h_dump_count[0];
+    for (int i = 1; i < NR; i++) {
+      cnt0_min = h_dump_count[i] < cnt0_min ? h_dump_count[i] : cnt0_min;
+      cnt0_max = h_dump_count[i] > cnt0_max ? h_dump_count[i] : cnt0_max;
+    }
+  }
+  std::vector<int32_t> cnt0;
+  if (windows) cnt0.assign(h_dump_count ? h_dump_count : nullptr, h_dump_count ? h_dump_count + NR : nullptr);
+  const double rec_per_block = (double)nsamp * 1000.0 / h->cfg.samp_rate;  // one dump per code period (1 ms)
+  const long long MARGIN = 16;
+  auto win_lo = [&](long long b0) {
+    const long long v = cnt0_min + (long long)floor((double)b0 * rec_per_block) - MARGIN;
+    return v < 0 ? 0ll : (v > dump_cap ? (long long)dump_cap : v);
+  };
+  auto win_hi = [&](long long b1, bool last_chunk) {
+    const long long v = cnt0_max + (long long)ceil((double)b1 * rec_per_block) + MARGIN;
+    return (last_chunk || v > dump_cap) ? (long long)dump_cap : v;
+  };
+  cudaStream_t s_back = h->s_back;
   if (!rc) TRY_(cudaEventRecord(h->ev0, s_comp));
   int c = 0;
   for (long long b0 = 0; b0 < nblocks && !rc; b0 += chunk, c++) {
@@ -406,15 +464,48 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
     TRY_(cudaEventRecord(ev_copied[buf], s_copy));
     TRY_(cudaStreamWaitEvent(s_comp, ev_copied[buf], 0));
     if (!rc) rc = track_launch(h, 0, S, d_stage[buf], dstride, fmt, nsamp, nb, 1, d_dumps, want ? dump_cap : 0, d_cnt, s_comp);
+    if (windows && !rc)  // exact counts after this chunk: 4 bytes per channel, in stream order right behind its kernels
+      TRY_(cudaMemcpyAsync(h->h_snap + (size_t)c * NR, d_cnt, sizeof(int32_t) * NR, cudaMemcpyDeviceToHost, s_comp));
     TRY_(cudaEventRecord(ev_used[buf], s_comp));
+    if (windows && !rc) {
+      const long long lo = win_lo(b0), hi = win_hi(b0 + nb, b0 + nb >= nblocks);
+      TRY_(cudaStreamWaitEvent(s_back, ev_used[buf], 0));
+      if (hi > lo)
+        TRY_(cudaMemcpy2DAsync(h_dumps + lo, sizeof(gnssb200_dump) * (size_t)dump_cap, d_dumps + lo, sizeof(gnssb200_dump) * (size_t)dump_cap,
+                               sizeof(gnssb200_dump) * (size_t)(hi - lo), NR, cudaMemcpyDeviceToHost, s_back));
+    }
   }
   if (!rc) TRY_(cudaEventRecord(h->ev1, s_comp));
   if (!rc && want) {
-    TRY_(cudaMemcpyAsync(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost, s_comp));
+    if (!windows)
+      TRY_(cudaMemcpyAsync(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost, s_comp));
     if (h_dump_count) TRY_(cudaMemcpyAsync(h_dump_count, d_cnt, sizeof(int32_t) * S * NCH, cudaMemcpyDeviceToHost, s_comp));
   }
   if (s_comp) TRY_(cudaStreamSynchronize(s_comp));
   if (s_copy) TRY_(cudaStreamSynchronize(s_copy));
+  if (s_back) TRY_(cudaStreamSynchronize(s_back));
+  if (windows && !rc) {
+    // every chunk's records [count before, count after) must lie inside the window copied after that chunk
+    bool ok = true;
+    long long b0 = 0;
+    for (long long cc = 0; cc < nchunks && ok; cc++, b0 += chunk) {
+      const long long nb = (nblocks - b0 < chunk) ? nblocks - b0 : chunk;
+      const long long lo = win_lo(b0), hi = win_hi(b0 + nb, b0 + nb >= nblocks);
+      const int32_t *after = h->h_snap + (size_t)cc * NR;
+      const int32_t *before = cc ? h->h_snap + (size_t)(cc - 1) * NR : (cnt0.empty() ? nullptr : cnt0.data());
+      for (int i = 0; i < NR; i++) {
+        const long long f = before ? before[i] : 0, t = after[i];
+        if (t > f && (f < lo || t > hi)) {
+          ok = false;
+          break;
+        }
+      }
+    }
+    if (!ok) {
+      h->back_fallbacks++;
+      TRY_(cudaMemcpy(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost));
+    }
+  }
 #undef TRY_
   return rc;
 }

@@ -45,6 +45,11 @@ struct gnssb200_handle {
   size_t stage_cnt_cap;
   cudaStream_t s_copy, s_comp;
   cudaEvent_t ev_copied[2], ev_used[2];
+  cudaStream_t s_back;        // device -> host stream of the dump-record windows (gnssb200_track_run_host)
+  int32_t *h_snap;            // pinned: dump counts after every chunk
+  size_t h_snap_cap;
+  long long stage_blocks;     // blocks per stream and staging chunk; 0 = automatic (gnssb200_set_stage_blocks)
+  long long back_fallbacks;   // host-buffer runs that had to repeat the dump read-back in one piece
 };
 
 // track.cu

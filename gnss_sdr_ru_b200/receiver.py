@@ -134,6 +134,13 @@ class TrackingEngine:
         check(self.L.gnssb200_download_rx(self.h, 0, self.n_streams, C.addressof(self.rx)), "gnssb200_download_rx")
 
     # ---- runs ----------------------------------------------------------------------------
+    def set_stage_blocks(self, blocks: int):
+        """blocks per stream and staging chunk of run_host (0 = automatic); results do not depend on it"""
+        check(self.L.gnssb200_set_stage_blocks(self.h, blocks), "gnssb200_set_stage_blocks")
+
+    def readback_fallbacks(self) -> int:
+        return int(self.L.gnssb200_readback_fallbacks(self.h))
+
     def run_host(self, iq: np.ndarray, nblocks: int, nsamp: int = NSAMP_DEFAULT, fmt: int = abi.FMT_INT8_IQ,
                  dump_cap: int = 0):
         """iq: (S, bytes) host array.  Returns (dumps[S,12,cap], counts[S,12]) when dump_cap > 0."""

@@ -204,6 +204,14 @@ int gnssb200_acq_serial(gnssb200_handle *h, const void *d_if, int fmt, int64_t n
  * not depend on it. */
 int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks);
 
+/* Host-buffer pipeline of gnssb200_track_run_host: blocks per stream and staging chunk (0 = automatic, about 384
+ * blocks, at least 32 MiB per chunk); results do not depend on it.  The dump records of a multi-chunk run are read
+ * back window by window while later chunks are still running when h_dumps is pinned (or registered) host memory;
+ * gnssb200_readback_fallbacks counts the runs whose records did not stay inside the predicted windows and were
+ * read back again in one piece (correct either way, see csrc/api.cu). */
+int gnssb200_set_stage_blocks(gnssb200_handle *h, int64_t blocks);
+int64_t gnssb200_readback_fallbacks(const gnssb200_handle *h);
+
 /* Number of kernels this library has launched since open (bench.py reports it as gpu_launches). */
 int64_t gnssb200_launch_count(const gnssb200_handle *h);
 /* Device time (ms, CUDA events on the launching stream) of the most recent track/acq kernel

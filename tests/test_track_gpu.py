@@ -322,3 +322,48 @@ def test_config5_width_kernels_agree():
     b = run(333, 1)
     c = run(0, 0)
     assert a == b == c and a[1] > 400000
+
+
+def _run_host_pinned(eng, recs, nblk, cap, cnt_init=None):
+    """gnssb200_track_run_host with PINNED result buffers (the windowed read-back only engages for those)"""
+    import torch
+
+    S = eng.n_streams
+    dt = np.dtype(abi.DUMP_DTYPE)
+    raw = torch.zeros((S, 12, cap * dt.itemsize), dtype=torch.uint8).pin_memory()
+    cnt = torch.zeros((S, 12), dtype=torch.int32).pin_memory()
+    if cnt_init is not None:
+        cnt.copy_(torch.from_numpy(cnt_init))
+    buf = np.ascontiguousarray(recs)
+    rc = eng.L.gnssb200_track_run_host(eng.h, buf.ctypes.data, buf.strides[0], abi.FMT_INT8_IQ, NS, nblk, raw.data_ptr(), cap, cnt.data_ptr())
+    assert rc == 0
+    return raw.numpy().view(dt).reshape(S, 12, cap), cnt.numpy().copy()
+
+
+@pytest.mark.parametrize("code_f, expect_fallback", [(None, False), (2 * 1023000.0, True)])
+def test_host_pipeline_windowed_readback(oracle_lib, track_record, code_f, expect_fallback):
+    """Multi-chunk host run (16-block chunks, pinned buffers): dump records come back window by window while later chunks
+    run; records, counts and final state equal the oracle's.  With a 0.5-ms code period the records leave the predicted
+    windows: the run must notice, read back in one piece and still be exact."""
+    rec, _ = track_record
+    n, S, cap = 300, 3, 900
+    over = dict(tic_period=0.0123, acq_thresh=1100)
+    if code_f is not None:
+        over["gps_code_f"] = code_f
+    recs = np.stack([np.roll(rec[: 2 * NS * n], 2 * 997 * s) for s in range(S)])
+    eng, orcs = _setup_pair(oracle_lib, n_streams=S, cfg_over=over)
+    eng.set_stage_blocks(16)
+    before = eng.readback_fallbacks()
+    d, c = _run_host_pinned(eng, recs[:, : 2 * NS * 200], 200, cap)
+    # resumed: the second call starts from the first call's counts and appends
+    d2, c2 = _run_host_pinned(eng, recs[:, 2 * NS * 200 :], n - 200, cap, cnt_init=c)
+    eng.download()
+    assert (eng.readback_fallbacks() - before > 0) == expect_fallback
+    for s, o in enumerate(orcs):
+        _, od, oc = o.run(recs[s], NS, n, dump_cap=cap)
+        assert np.array_equal(c2[s], oc), (c2[s], oc)
+        for ch in range(12):
+            k1 = c[s, ch]
+            assert np.array_equal(d[s, ch, :k1], od[ch, :k1]), f"first call, stream {s} channel {ch}"
+            assert np.array_equal(d2[s, ch, k1 : oc[ch]], od[ch, k1 : oc[ch]]), f"second call, stream {s} channel {ch}"
+        assert _rx_bytes(eng.rx[s]) == _rx_bytes(o.rx)
