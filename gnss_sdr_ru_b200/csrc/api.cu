@@ -418,7 +418,7 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
   // windowed read-back of the dump records: only into pinned host memory
   const long long nchunks = nblocks > 0 ? (nblocks + chunk - 1) / chunk : 0;
   const int NR = S * NCH;
-  bool windows = want && !rc && nchunks > 1;
+  bool windows = want && !rc && nchunks > 1 && h->cfg.samp_rate > 0;
   if (windows) {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, h_dumps) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
