@@ -448,9 +448,9 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
     const long long v = cnt0_min + (long long)floor((double)b0 * rec_per_block) - MARGIN;
     return v < 0 ? 0ll : (v > dump_cap ? (long long)dump_cap : v);
   };
-  auto win_hi = [&](long long b1, bool last_chunk) {
+  auto win_hi = [&](long long b1) {
     const long long v = cnt0_max + (long long)ceil((double)b1 * rec_per_block) + MARGIN;
-    return (last_chunk || v > dump_cap) ? (long long)dump_cap : v;
+    return v > dump_cap ? (long long)dump_cap : v;
   };
   cudaStream_t s_back = h->s_back;
   if (!rc) TRY_(cudaEventRecord(h->ev0, s_comp));
@@ -468,7 +468,7 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
       TRY_(cudaMemcpyAsync(h->h_snap + (size_t)c * NR, d_cnt, sizeof(int32_t) * NR, cudaMemcpyDeviceToHost, s_comp));
     TRY_(cudaEventRecord(ev_used[buf], s_comp));
     if (windows && !rc) {
-      const long long lo = win_lo(b0), hi = win_hi(b0 + nb, b0 + nb >= nblocks);
+      const long long lo = win_lo(b0), hi = win_hi(b0 + nb);
       TRY_(cudaStreamWaitEvent(s_back, ev_used[buf], 0));
       if (hi > lo)
         TRY_(cudaMemcpy2DAsync(h_dumps + lo, sizeof(gnssb200_dump) * (size_t)dump_cap, d_dumps + lo, sizeof(gnssb200_dump) * (size_t)dump_cap,
@@ -490,7 +490,7 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
     long long b0 = 0;
     for (long long cc = 0; cc < nchunks && ok; cc++, b0 += chunk) {
       const long long nb = (nblocks - b0 < chunk) ? nblocks - b0 : chunk;
-      const long long lo = win_lo(b0), hi = win_hi(b0 + nb, b0 + nb >= nblocks);
+      const long long lo = win_lo(b0), hi = win_hi(b0 + nb);
       const int32_t *after = h->h_snap + (size_t)cc * NR;
       const int32_t *before = cc ? h->h_snap + (size_t)(cc - 1) * NR : (cnt0.empty() ? nullptr : cnt0.data());
       for (int i = 0; i < NR; i++) {
