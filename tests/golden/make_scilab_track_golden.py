@@ -1,6 +1,7 @@
-"""Extracts the reference's own saved tracking run into tests/golden/scilab_track_golden.npz:
-SCI/GLONASS/L1/trackingResults.dat (Scilab 5 save() of trackResults, settings, acqResults, channel written by
-postProcessing.sce:143 after tracking 1500 ms of a real GLONASS L1 recording), read with oracle/scilab_save.py.
+"""Extracts the reference's own saved tracking runs into tests/golden/scilab_track_golden.npz (and ..._l2.npz):
+SCI/GLONASS/L1/trackingResults.dat and SCI/GLONASS/L2/trackingResults.dat (Scilab 5 save() of trackResults, settings,
+acqResults, channel written by postProcessing.sce:143 after tracking 1500 ms of a real GLONASS recording on the L1 and
+on the L2 front-end settings), read with oracle/scilab_save.py.
 Run in the container that has /root/reference:   python tests/golden/make_scilab_track_golden.py"""
 import os
 import sys
@@ -12,6 +13,7 @@ sys.path.insert(0, ROOT)
 from oracle import scilab_save  # noqa: E402
 
 SRC = "/root/reference/trunk/GNSS_SOFTWARE_RECEIVERS/POSTPROCESSING_SCILAB_RECEIVERS/GLONASS/L1/trackingResults.dat"
+SRC_L2 = SRC.replace("/L1/", "/L2/")
 
 
 def extract(path=SRC):
@@ -34,6 +36,7 @@ def extract(path=SRC):
 
 
 if __name__ == "__main__":
-    o = extract()
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "scilab_track_golden.npz"), **o)
-    print("written", len(o), "arrays;", int(o["settings_msToProcess"]), "ms, FCH", o["channel_FCH"])
+    for src, name in ((SRC, "scilab_track_golden.npz"), (SRC_L2, "scilab_track_golden_l2.npz")):
+        o = extract(src)
+        np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), name), **o)
+        print(name, "written", len(o), "arrays;", int(o["settings_msToProcess"]), "ms, FCH", o["channel_FCH"])
