@@ -178,7 +178,11 @@ int gnssb200_track_run(gnssb200_handle *h, const void *d_if, size_t stream_strid
                        int nsamp, int64_t nblocks, gnssb200_dump *d_dumps, int dump_cap,
                        int32_t *d_dump_count, void *cuda_stream);
 
-/* Convenience: same from host memory (copies in, runs, copies records out, synchronises). */
+/* The same from host memory (copies in, runs, copies records out, synchronises): the record is staged through two
+ * device buffers chunk by chunk, the copy of chunk c+1 under the kernels of chunk c; h_dumps / h_dump_count
+ * (in: counts to continue from, may be NULL = 0; out: counts after the run) are host arrays laid out like their
+ * device counterparts above.  Pinned (cudaHostAlloc / cudaHostRegister) buffers give full PCIe speed and let the dump
+ * records travel back while later chunks still run; pageable buffers give the same results without the overlap. */
 int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, size_t stream_stride_bytes, int fmt,
                             int nsamp, int64_t nblocks, gnssb200_dump *h_dumps, int dump_cap,
                             int32_t *h_dump_count);
