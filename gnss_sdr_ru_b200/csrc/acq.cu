@@ -332,13 +332,10 @@ extern "C" int gnssb200_acq_search(gnssb200_handle *h, const gnssb200_acq_cfg *c
   const int n_bins = gnssb200_acq_num_bins(cfg);
   const int K = acq_blocks(cfg);
   const size_t smem = fft16k::SMEM_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(acq_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(acq_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(acq_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  // the opt-in is an attribute of the kernel on the current device: set it per call (a handle may live on any device)
+  CUDA_TRY(cudaFuncSetAttribute(acq_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(acq_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(acq_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // ---- twiddle tables (once) ----
   if (!w.d_tw16k) {
     std::vector<float2> t1(fft16k::M), t2(fft16k::R3);

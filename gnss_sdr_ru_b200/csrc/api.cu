@@ -132,6 +132,9 @@ extern "C" gnssb200_handle *gnssb200_open(int device, const gnssb200_cfg *cfg) {
       (e = cudaMemcpy(h->d_code_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
     gnssb200_set_error((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    cudaFree(h->d_code_table);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
     return nullptr;
   }
@@ -146,6 +149,7 @@ extern "C" void gnssb200_close(gnssb200_handle *h) {
   cudaFree(h->d_chan_flags);
   cudaFree(h->d_sched);
   cudaFree(h->d_code_table);
+  cudaFree(h->d_chips);
   for (int i = 0; i < 2; i++) {
     cudaFree(h->stage[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -278,6 +282,13 @@ extern "C" int gnssb200_acq_serial(gnssb200_handle *h, const void *d_if, int fmt
 extern "C" int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks) {
   if (!h || blocks < 0) return -1;
   h->track_slice = blocks;
+  return 0;
+}
+
+extern "C" int gnssb200_set_track_variant(gnssb200_handle *h, int form, int occ) {
+  if (!h || form < 0 || form > 5 || occ < 0 || occ > 8) return -1;
+  h->track_form = form;
+  h->track_occ = occ;
   return 0;
 }
 
@@ -433,20 +444,30 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
     h->h_snap_cap = rc ? 0 : sizeof(int32_t) * NR * (size_t)nchunks;
   }
   long long cnt0_min = 0, cnt0_max = 0;  // counts the run starts from (host memory, readable now)
-  if (windows && h_dump_count) {
-    cnt0_min = cnt0_max = h_dump_count[0];
-    for (int i = 1; i < NR; i++) {
-      cnt0_min = h_dump_count[i] < cnt0_min ? h_dump_count[i] : cnt0_min;
-      cnt0_max = h_dump_count[i] > cnt0_max ? h_dump_count[i] : cnt0_max;
+  std::vector<int32_t> cnt0;
+  // A continued run (h_dump_count given) only appends: the records a channel already holds, [0, cnt0[i]), stay the
+  // caller's.  Nothing below column cnt0_min is copied back; what the copies overwrite between cnt0_min and a
+  // channel's own cnt0[i] (the staging buffer need not hold those records) is saved here and put back at the end.
+  std::vector<gnssb200_dump> keep;
+  if (want && h_dump_count) {
+    cnt0.assign(h_dump_count, h_dump_count + NR);
+    cnt0_min = cnt0_max = cnt0[0] < 0 ? 0 : (cnt0[0] > dump_cap ? dump_cap : cnt0[0]);
+    for (int i = 0; i < NR; i++) {
+      const long long v = cnt0[i] < 0 ? 0 : (cnt0[i] > dump_cap ? dump_cap : cnt0[i]);
+      cnt0_min = v < cnt0_min ? v : cnt0_min;
+      cnt0_max = v > cnt0_max ? v : cnt0_max;
+    }
+    for (int i = 0; i < NR; i++) {
+      const long long v = cnt0[i] < 0 ? 0 : (cnt0[i] > dump_cap ? dump_cap : cnt0[i]);
+      keep.insert(keep.end(), h_dumps + (size_t)i * dump_cap + cnt0_min, h_dumps + (size_t)i * dump_cap + v);
     }
   }
-  std::vector<int32_t> cnt0;
-  if (windows) cnt0.assign(h_dump_count ? h_dump_count : nullptr, h_dump_count ? h_dump_count + NR : nullptr);
+  const long long col0 = cnt0_min;  // first column any read-back touches
   const double rec_per_block = (double)nsamp * 1000.0 / h->cfg.samp_rate;  // one dump per code period (1 ms)
   const long long MARGIN = 16;
   auto win_lo = [&](long long b0) {
     const long long v = cnt0_min + (long long)floor((double)b0 * rec_per_block) - MARGIN;
-    return v < 0 ? 0ll : (v > dump_cap ? (long long)dump_cap : v);
+    return v < col0 ? col0 : (v > dump_cap ? (long long)dump_cap : v);
   };
   auto win_hi = [&](long long b1) {
     const long long v = cnt0_max + (long long)ceil((double)b1 * rec_per_block) + MARGIN;
@@ -477,8 +498,9 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
   }
   if (!rc) TRY_(cudaEventRecord(h->ev1, s_comp));
   if (!rc && want) {
-    if (!windows)
-      TRY_(cudaMemcpyAsync(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost, s_comp));
+    if (!windows && dump_cap > col0)
+      TRY_(cudaMemcpy2DAsync(h_dumps + col0, sizeof(gnssb200_dump) * (size_t)dump_cap, d_dumps + col0, sizeof(gnssb200_dump) * (size_t)dump_cap,
+                             sizeof(gnssb200_dump) * (size_t)(dump_cap - col0), NR, cudaMemcpyDeviceToHost, s_comp));
     if (h_dump_count) TRY_(cudaMemcpyAsync(h_dump_count, d_cnt, sizeof(int32_t) * S * NCH, cudaMemcpyDeviceToHost, s_comp));
   }
   if (s_comp) TRY_(cudaStreamSynchronize(s_comp));
@@ -503,7 +525,16 @@ extern "C" int gnssb200_track_run_host(gnssb200_handle *h, const void *h_if, siz
     }
     if (!ok) {
       h->back_fallbacks++;
-      TRY_(cudaMemcpy(h_dumps, d_dumps, sizeof(gnssb200_dump) * (size_t)S * NCH * dump_cap, cudaMemcpyDeviceToHost));
+      if (dump_cap > col0)
+        TRY_(cudaMemcpy2D(h_dumps + col0, sizeof(gnssb200_dump) * (size_t)dump_cap, d_dumps + col0, sizeof(gnssb200_dump) * (size_t)dump_cap,
+                          sizeof(gnssb200_dump) * (size_t)(dump_cap - col0), NR, cudaMemcpyDeviceToHost));
+    }
+  }
+  if (!keep.empty()) {  // the caller's earlier records between cnt0_min and each channel's own start
+    size_t k = 0;
+    for (int i = 0; i < NR; i++) {
+      const long long v = cnt0[i] < 0 ? 0 : (cnt0[i] > dump_cap ? dump_cap : cnt0[i]);
+      for (long long j = cnt0_min; j < v; j++) h_dumps[(size_t)i * dump_cap + j] = keep[k++];
     }
   }
 #undef TRY_
@@ -582,8 +613,37 @@ extern "C" void Sim_GP2021_int(char *IF, long nsamp) {
     gnssb200_set_error(-5, "Sim_GP2021_int before correlator_init", __FILE__, __LINE__);
     dropin_die("Sim_GP2021_int");
   }
-  if (nsamp <= 0) {  // the reference's loops simply do not run; status words are still rewritten
-    REG_read[0x82] = 0;
+  if (nsamp <= 0) {
+    // No samples: the reference's sample loop does not run, but the call still moves the TIC counter
+    // (correlator.c:155-165), applies pending epoch loads (:175-180) and rewrites both status words (:309-315).
+    gnssb200_rx *rx = new gnssb200_rx;
+    if (gnssb200_download_rx(d.h, 0, 1, rx)) dropin_die("gnssb200_download_rx");
+    memcpy(rx->reg_read, REG_read, sizeof REG_read);
+    memcpy(rx->reg_write, REG_write, sizeof REG_write);
+    long long tic_count;
+    if (rx->tic < (long long)nsamp) {
+      tic_count = rx->tic;
+      rx->tic += d.h->cfg.tic_ref - (long long)nsamp;
+    } else {
+      rx->tic -= (long long)nsamp;
+      tic_count = -1;
+    }
+    for (int ch = 0; ch < NCH; ch++) {
+      const int reg = ch << 3;
+      if (rx->reg_write[reg + 7] != -1) {
+        rx->reg_read[reg + 7] = rx->reg_write[reg + 7];
+        rx->corr[ch].ms_counter = rx->reg_write[reg + 7] & 0xff;
+        rx->corr[ch].bit_counter = rx->reg_write[reg + 7] >> 8;
+        rx->reg_write[reg + 7] = -1;
+      }
+    }
+    rx->reg_read[0x82] = 0;
+    rx->reg_read[0x83] = tic_count > -1 ? 0x2000 : 0;
+    const int rc = gnssb200_upload_rx(d.h, 0, 1, rx);
+    memcpy(REG_read, rx->reg_read, sizeof REG_read);
+    memcpy(REG_write, rx->reg_write, sizeof REG_write);
+    delete rx;
+    if (rc) dropin_die("gnssb200_upload_rx");
     return;
   }
   const int fmt = (&use_iq_processing && !use_iq_processing) ? GNSSB200_FMT_INT8_I : GNSSB200_FMT_INT8_IQ;

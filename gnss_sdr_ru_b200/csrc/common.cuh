@@ -29,8 +29,10 @@ struct gnssb200_handle {
   gnssb200_rx *d_rx;          // [n_streams]
   int32_t *d_chan_flags;      // [n_streams*12] bit0: dumped in the last block, bit1: halted
   long long track_slice;      // blocks per work-queue slice of the tracking kernel; 0 = automatic (gnssb200_set_track_slice)
+  int track_form, track_occ;  // kernel form / occupancy variant forced by gnssb200_set_track_variant (0 = automatic)
   void *d_sched;              // work queue of track_ws_kernel: headers / TIC counters / slots / dump counters per channel
   uint32_t *d_code_table;     // [TABLE_ENTRIES+1] packed E | P<<8 | L<<16 (int8 each), last entry 0
+  int8_t *d_chips;            // [33][1024] chips as +-1: row 0 GLONASS ST code, rows 1..32 GPS C/A (chip_table, synth.cu)
   cudaEvent_t ev0, ev1;
   long long launches;
   float serial_ms;            // device time of the last gnssb200_acq_serial run
@@ -58,6 +60,9 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
                  int32_t *d_dump_count, cudaStream_t st);
 void build_code_table_host(uint32_t *table /* TABLE_ENTRIES+1 */);
 size_t track_sched_bytes(int n_streams);
+
+// synth.cu: the handle's chip table (built on first use, freed by gnssb200_close)
+int chip_table(gnssb200_handle *h, const int8_t **d_chips);
 
 // acq.cu
 void acq_free_workspace(gnssb200_handle *h);

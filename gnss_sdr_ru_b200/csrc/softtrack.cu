@@ -182,32 +182,15 @@ __global__ void __launch_bounds__(512) softtrack_kernel(const FtrkArgs a) {
 extern "C" int gnssb200_softtrack(gnssb200_handle *h, const gnssb200_softtrack_cfg *cfg, const void *d_iq, int64_t n_samples,
                                   const gnssb200_softtrack_chan *chans, int n_ch, double *d_out, int32_t *d_ms_done,
                                   void *cuda_stream) {
-  if (!h || !cfg || !d_iq || !chans || n_ch <= 0 || !d_out || !d_ms_done || cfg->ms_to_process <= 0) {
+  if (!h || !cfg || !d_iq || !chans || n_ch <= 0 || !d_out || !d_ms_done || cfg->ms_to_process <= 0 ||
+      (cfg->code_length != 511 && cfg->code_length != 1023)) {  // the kernel's chip buffer holds one ST or C/A period
     gnssb200_set_error(-20, "gnssb200_softtrack: bad arguments", __FILE__, __LINE__);
     return -20;
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  static int8_t *d_chips = nullptr;
-  static int chips_dev = -1;
-  if (!d_chips || chips_dev != h->device) {
-    std::vector<int8_t> chips(33 * 1024, 0);
-    std::vector<uint32_t> table(TABLE_ENTRIES + 1);
-    build_code_table_host(table.data());
-    for (int prn = 1; prn <= 32; prn++)
-      for (int k = 0; k < 1023; k++) chips[prn * 1024 + k] = (int8_t)(table[prn * HALF_CHIPS + 2 * k] & 0xff);
-    int reg[9];
-    for (int i = 0; i < 9; i++) reg[i] = 1;
-    for (int k = 0; k < 511; k++) {  // generateSTcode.sci:35-42
-      chips[k] = (int8_t)(2 * reg[6] - 1);
-      const int fb = reg[4] ^ reg[8];
-      for (int i = 8; i > 0; i--) reg[i] = reg[i - 1];
-      reg[0] = fb;
-    }
-    CUDA_TRY(cudaMalloc(&d_chips, chips.size()));
-    CUDA_TRY(cudaMemcpy(d_chips, chips.data(), chips.size(), cudaMemcpyHostToDevice));
-    chips_dev = h->device;
-  }
+  const int8_t *d_chips = nullptr;
+  if (int rc = chip_table(h, &d_chips)) return rc;
   const bool glo = cfg->system == GNSSB200_SYS_GLONASS;
   std::vector<FtrkChanDev> hc(n_ch);
   for (int i = 0; i < n_ch; i++) {

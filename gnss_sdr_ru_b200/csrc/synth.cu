@@ -93,18 +93,9 @@ __global__ void synth_kernel(uint8_t *out, size_t stride, int fmt, int64_t n_sam
   }
 }
 
-extern "C" int gnssb200_synth(gnssb200_handle *h, void *d_out, size_t stride, int fmt, int n_streams, int64_t n_samples,
-                              const gnssb200_synth_sat *sats, int n_sats, uint64_t seed, void *cuda_stream) {
-  if (!h || n_streams <= 0 || n_samples <= 0 || (n_samples & 3) || fmt == GNSSB200_FMT_INT8_I) {
-    gnssb200_set_error(-6, "gnssb200_synth: bad arguments (n_samples must be a multiple of 4)", __FILE__, __LINE__);
-    return -6;
-  }
-  CUDA_TRY(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  // chip table: rows 1..32 GPS C/A (same generator as the correlator table), row 0 GLONASS ST code
-  static int8_t *d_chips = nullptr;
-  static int chips_dev = -1;
-  if (!d_chips || chips_dev != h->device) {
+// chip table of a handle: rows 1..32 GPS C/A (same generator as the correlator table), row 0 GLONASS ST code
+int chip_table(gnssb200_handle *h, const int8_t **out) {
+  if (!h->d_chips) {
     std::vector<int8_t> chips(33 * 1024, 0);
     std::vector<uint32_t> table(TABLE_ENTRIES + 1);
     build_code_table_host(table.data());
@@ -120,10 +111,29 @@ extern "C" int gnssb200_synth(gnssb200_handle *h, void *d_out, size_t stride, in
         reg[0] = fb;
       }
     }
-    CUDA_TRY(cudaMalloc(&d_chips, chips.size()));
-    CUDA_TRY(cudaMemcpy(d_chips, chips.data(), chips.size(), cudaMemcpyHostToDevice));
-    chips_dev = h->device;
+    int8_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, chips.size()));
+    cudaError_t e = cudaMemcpy(d, chips.data(), chips.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(d);
+      CUDA_TRY(e);
+    }
+    h->d_chips = d;
   }
+  *out = h->d_chips;
+  return 0;
+}
+
+extern "C" int gnssb200_synth(gnssb200_handle *h, void *d_out, size_t stride, int fmt, int n_streams, int64_t n_samples,
+                              const gnssb200_synth_sat *sats, int n_sats, uint64_t seed, void *cuda_stream) {
+  if (!h || n_streams <= 0 || n_samples <= 0 || (n_samples & 3) || fmt == GNSSB200_FMT_INT8_I) {
+    gnssb200_set_error(-6, "gnssb200_synth: bad arguments (n_samples must be a multiple of 4)", __FILE__, __LINE__);
+    return -6;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int8_t *d_chips = nullptr;
+  if (int rc = chip_table(h, &d_chips)) return rc;
   std::vector<SynthSat> hs((size_t)n_streams * n_sats);
   std::vector<uint8_t> pool;  // explicit data bits of all emitters, back to back
   for (size_t i = 0; i < hs.size(); i++) {

@@ -182,11 +182,11 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
   const int use_tma = (aligned && !no_tma && nsamp <= 256 * spt && blk_bytes <= 16384) ? 1 : 0;
   const int tile_bytes = use_tma ? (int)((blk_bytes + 127) & ~(size_t)127) : 0;
   const size_t dyn = (size_t)2 * tile_bytes + ((use_tma && fmt == GNSSB200_FMT_PACKED2) ? 128 * 32 * 4 : 0);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // the opt-in is per device
+  if (h->device < 0 || h->device >= 64 || !attr_done[h->device]) {
     CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 + 256));
     CUDA_TRY(cudaFuncSetAttribute(track_loop_kernel<256, 2, GNSSB200_FMT_PACKED2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16384 + 256));
-    attr_done = true;
+    if (h->device >= 0 && h->device < 64) attr_done[h->device] = true;
   }
   static int force_occ = -1;  // GNSSB200_TRACK_OCC: force the resident-CTAs-per-SM variant (experiments)
   if (force_occ < 0) {
@@ -201,18 +201,32 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     const char *e = getenv("GNSSB200_TRACK_WS");
     use_ws = e ? atoi(e) : 1;
   }
-  if (use_ws && hot) {  // warp-specialised variant: correlator warps + control lane
+  // gnssb200_set_track_variant: 0 automatic, 1 the barrier-synchronised kernel, 2 fixed sample runs, 3/4/5 half-chip
+  // segments with 96 / 192 / 384 correlator threads
+  static int env_form = -1;  // GNSSB200_TRACK_FORM: the same selection for handles that did not choose (experiments)
+  if (env_form < 0) {
+    const char *e = getenv("GNSSB200_TRACK_FORM");
+    env_form = e ? atoi(e) : 0;
+  }
+  const int form = h->track_form ? h->track_form : env_form;
+  if (form != 1 && use_ws && hot) {  // warp-specialised variant: correlator warps + control lane
     constexpr int DSM_I8 = 2 * 16384 + 256, DSM_PK = 3 * 16384 + 256;
-    static bool aws = false;
-    if (!aws) {
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
-      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
-      aws = true;
+    // the shared-memory opt-in is a per-device attribute of each kernel
+    static bool aws[64] = {};
+    if (h->device < 0 || h->device >= 64 || !aws[h->device]) {
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 96, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 96, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 96, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 192, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      if (h->device >= 0 && h->device < 64) aws[h->device] = true;
     }
     // Work queue: every channel's blocks are cut into slices of slice_blocks; one CTA per (channel, slice)
     // item, items handed out through the FIFO so that a channel's slices run in order.
@@ -241,21 +255,52 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     }
     const unsigned items = (unsigned)grid * nslices;
     // CTAs per SM the channels ask for -> variant (registers / samples per thread)
-    const int per_sm = force_occ ? force_occ : (grid + sms - 1) / sms;
+    const int occ = h->track_occ ? h->track_occ : force_occ;
+    const int per_sm = occ ? occ : (grid + sms - 1) / sms;
+    // Half-chip segments need 7 or 8 samples per half chip: decided from the nominal code NCO word of this
+    // configuration (a block whose word left that range is still handled, sample by sample, inside the kernel).
+    bool seg = false;
+    if (fmt == GNSSB200_FMT_PACKED2 && form != 2) {
+      const int shk = 32 - h->cfg.code_nco_bits;
+      if (shk >= 0 && shk < 32) {
+        const long long w = (long long)((double)((long long)h->cfg.gps_code_ref << shk) * h->cfg.clock_mult);  // gp2021.c:100-118
+        const unsigned long long kinc = ((unsigned long long)(w & 0xffffffffll)) << 1;
+        seg = kinc >= (1ull << 29) && 7ull * kinc <= (1ull << 32);
+      }
+      static int env_seg = -1;
+      if (env_seg < 0) {
+        const char *e = getenv("GNSSB200_TRACK_SEG");
+        env_seg = e ? atoi(e) : 1;
+      }
+      if (!env_seg && form == 0) seg = false;
+      if (form >= 3) seg = true;  // forced: out-of-range blocks take the per-sample form inside the kernel
+    }
+    const size_t dyn_seg = dyn + 2048;  // slack to start the mixer table on a 2048-byte boundary
     if (fmt == GNSSB200_FMT_INT8_IQ && per_sm >= 3)
-      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
-      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
-    else if (force_occ == 6)
-      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
-    else if (per_sm >= 5)  // five resident CTAs of 72 registers beat six of 64 (spills) by 1-4 % under the work queue
-      track_ws_kernel<5, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
-    else if (per_sm == 4)
-      track_ws_kernel<4, GNSSB200_FMT_PACKED2, 64><<<items, 160, dyn, st>>>(a, tile_bytes);
-    else if (per_sm == 3)
-      track_ws_kernel<3, GNSSB200_FMT_PACKED2, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
+    else if (seg && (form == 5 || (form == 0 && per_sm <= 1)))
+      track_ws_kernel<2, GNSSB200_FMT_PACKED2, 384, 3><<<items, 416, dyn_seg, st>>>(a, tile_bytes);
+    else if (seg && (form == 4 || (form == 0 && per_sm <= 2)))
+      track_ws_kernel<3, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
+    else if (seg && per_sm >= 6)
+      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 96, 11><<<items, 128, dyn_seg, st>>>(a, tile_bytes);
+    else if (seg && per_sm == 5)
+      track_ws_kernel<5, GNSSB200_FMT_PACKED2, 96, 11><<<items, 128, dyn_seg, st>>>(a, tile_bytes);
+    else if (seg)
+      track_ws_kernel<4, GNSSB200_FMT_PACKED2, 96, 11><<<items, 128, dyn_seg, st>>>(a, tile_bytes);
+    // fixed sample runs: 64 samples per thread only when they tile the block (a thread always takes its whole run)
+    else if (occ == 6 && nsamp % 64 == 0)
+      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 128><<<items, 160, dyn, st>>>(a, tile_bytes);
+    else if (per_sm >= 5 && nsamp % 64 == 0)  // five resident CTAs of 72 registers beat six of 64 (spills) by 1-4 % under the work queue
+      track_ws_kernel<5, GNSSB200_FMT_PACKED2, 128><<<items, 160, dyn, st>>>(a, tile_bytes);
+    else if (per_sm == 4 && nsamp % 64 == 0)
+      track_ws_kernel<4, GNSSB200_FMT_PACKED2, 128><<<items, 160, dyn, st>>>(a, tile_bytes);
+    else if (per_sm >= 3)
+      track_ws_kernel<3, GNSSB200_FMT_PACKED2, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
     else
-      track_ws_kernel<2, GNSSB200_FMT_PACKED2, 32><<<items, 288, dyn, st>>>(a, tile_bytes);
+      track_ws_kernel<2, GNSSB200_FMT_PACKED2, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
   } else
   if (hot && fmt == GNSSB200_FMT_INT8_IQ)  // GNSSB200_TRACK_WS=0: the barrier-synchronised predecessor, kept for A/B runs
     track_loop_kernel<256, 2, GNSSB200_FMT_INT8_IQ, true><<<grid, threads, dyn, st>>>(a, tile_bytes);

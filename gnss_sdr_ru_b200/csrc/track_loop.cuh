@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   StepParams sp = sp_s;
   int carry[6] = {0, 0, 0, 0, 0, 0};
   unsigned long long nk = (unsigned long long)a.nsamp * sp.kinc, nc = (unsigned long long)a.nsamp * sp.cinc;
-  for (long long b = 0; b < a.nblocks; b++) {
+  long long prefetched = -1;  // last block whose TMA load was issued (uniform over the CTA)
+  long long b = 0;
+  for (; b < a.nblocks; b++) {
 #ifdef TRACK_PROFILE
     long long c0 = clock64();
 #endif
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
         mbar_expect_tx(&mbar[(b + 1) & 1], (uint32_t)blk_bytes);
         tma_load_1d(tiles + (size_t)((b + 1) & 1) * tile_bytes, blk + blk_bytes, (uint32_t)blk_bytes, &mbar[(b + 1) & 1]);
       }
+      if (b + 1 < a.nblocks) prefetched = b + 1;
 #ifdef TRACK_PROFILE
       long long w0c = clock64();
 #endif
@@ -388,6 +391,8 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   }
 #endif
 
+  // the loop left early (halt) with the next block's load still in flight: it must land before the CTA exits
+  if (use_tma && b < a.nblocks && prefetched == b) mbar_wait(&mbar[b & 1], (uint32_t)((b >> 1) & 1));
   if (tid == 0) {
     rx->chan[ch] = cs.k;
     rx->corr[ch] = cs.g;

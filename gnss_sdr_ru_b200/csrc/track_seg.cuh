@@ -1,0 +1,221 @@
+// track_seg.cuh -- the half-chip-segment form of the correlator inner loop (track_ws_kernel, packed 2+2-bit input).
+//
+// The reference multiplies every mixed sample by the three code bits (correlator.c:227-232).  The bits only change
+// when the code NCO wraps (:243-250), and a wrap starts a new half chip, so with S_m = sum of the mixer outputs of the
+// samples the block sees between wrap m and wrap m+1 ("segment" m)
+//     accum = sum_m bits[h(m)] * S_m                                        (exact: integer sums reordered)
+// A thread owns H consecutive segments instead of a fixed run of samples: per sample only the mixer look-up is
+// left (one table read, five address instructions), the three multiplies by E/P/L happen once per half chip, and the
+// per-sample question "did the code NCO wrap here" disappears: with 2^29 <= kinc and 7*kinc <= 2^32 every full
+// segment has 7 or 8 samples, decided by one carry of `ks + 7*kinc`.  Dump boundaries are wrap boundaries, so a
+// segment never straddles a dump.  What threads cannot own as whole segments -- the head segment (it began in the
+// previous block), the tail (cut by the block end) -- is evaluated one sample per lane by the closed forms.
+#pragma once
+#include "track_common.cuh"
+
+#ifndef SEG_UNROLL
+#define SEG_UNROLL 1
+#endif
+
+struct __align__(16) BlockParams {
+  uint32_t cph0, kph0, cinc, kinc;
+  uint32_t hc0, w1, stale_idx, stale_bits;
+  int mode, event;
+  uint32_t wtot;  // code-NCO wraps over the block = index of the tail segment
+  uint32_t seg;   // 1: the segment form applies (kinc in range)
+  double dinv;    // 1.0 / kinc, correctly rounded
+  double pad;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t t;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(addr));
+  return t;
+}
+
+// kinc for which every full segment holds 7 or 8 samples: a segment starts with code phase ks < kinc and ends with
+// the sample whose step wraps, n = ceil((2^32 - ks) / kinc); n >= 7 for all ks < kinc iff 7*kinc <= 2^32, n <= 8 iff
+// 8*kinc >= 2^32
+__device__ __forceinline__ bool seg_kinc_ok(uint32_t kinc) { return kinc >= (1u << 29) && 7ull * kinc <= (1ull << 32); }
+
+// first sample of segment m >= 1: s = ceil((m*2^32 - kph0) / kinc) = floor((x - 0.5) / kinc) + 1 with x = m*2^32 -
+// kph0 >= 1.  In doubles: x - 0.5 is exact (x < 2^44), (x - 0.5)/kinc is at least 0.5/kinc > 2^-31 away from every
+// integer, the computed product is off by less than 2^13 * 2^-51 -- truncation gives the exact floor.
+__device__ __forceinline__ uint32_t seg_start(uint32_t m, double nk05 /* -kph0 - 0.5 */, double dinv) {
+  const double x = fma((double)m, 4294967296.0, nk05);
+  return (uint32_t)(x * dinv) + 1u;
+}
+
+// H whole segments starting at sample s: q = bit address of the sample's 4-bit code in shared memory (8 * byte
+// address of the tile + 4*s), cph / ks = carrier / code NCO phase at s (ks < kinc), hp = shared-memory byte address
+// of the first segment's code-table entry (consecutive entries follow), nvalid = segments that count.
+// Sums come back as two 16-bit lanes (ival + 65536*qval), |lane| <= 8*H*9.
+template <int H>
+__device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uint32_t ks, const uint32_t cinc, const uint32_t kinc,
+                                                   const uint32_t k7, const uint32_t hp, const int nvalid, const uint32_t vlut_lane,
+                                                   const PipeK K, int &accE, int &accP, int &accL) {
+  int aE = 0, aP = 0, aL = 0;
+  // Rolled on purpose: the body is ~75 instructions; unrolled H times every warp streams through > 10 KB of code per
+  // block and the warps of an SM, each somewhere else in it, keep missing the instruction cache (ncu: a sixth of the
+  // stalled warp-cycles were `no_instructions`).
+  constexpr int UNR = SEG_UNROLL;
+#pragma unroll UNR
+  for (int j = 0; j < H; j++) {
+    // eight 4-bit sample codes from bit address q (two aligned words, funnel shift by q mod 32)
+    const uint32_t a = (q >> 3) & ~3u;
+    const uint32_t lo = lds_u32(a), hi = lds_u32(a + 4);
+    const uint32_t wd = __funnelshift_r(lo, hi, q);
+    // 7 or 8 samples: the segment ends with the sample whose code step wraps
+    uint32_t u, c;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(u), "=r"(c) : "r"(ks), "r"(k7));
+    const bool eight = c == 0;
+    ks = eight ? u + kinc : u;
+    q += eight ? 32u : 28u;
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      // entry offset = (phase*16 + code) * 128 bytes + lane*4.  Code part on the ALU pipe (shift, and-or), LO
+      // phase (top three bits of the carrier NCO), its scaling and the NCO step as IMADs on the FMA pipe.
+      uint32_t sh;
+      if (k == 0)
+        sh = wd << 7;
+      else if (k == 1)
+        sh = wd << 3;
+      else
+        sh = wd >> (4 * k - 7);
+      uint32_t ca;
+      asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(ca) : "r"(sh), "r"(vlut_lane));  // (sh & 0x780) | vlut_lane
+      const uint32_t idx = __umulhi(cph, K.k8);
+      v[k] = (int)lds_u32(idx * K.k2048 + ca);
+      if (k < 7) cph = cinc * K.k1 + cph;
+    }
+    int S = v[0] + v[1] + v[2] + v[3] + v[4] + v[5] + v[6];
+    if (eight) {
+      S += v[7];
+      cph += cinc;
+    }
+    const uint32_t t = lds_u32(hp + 4u * (uint32_t)j);
+    if (j < nvalid) {
+      aE += sext8(t, 0) * S;
+      aP += sext8(t, 1) * S;
+      aL += sext8(t, 2) * S;
+    }
+  }
+  accE = aE;
+  accP = aP;
+  accL = aL;
+}
+
+// One sample from the closed forms (SURVEY.md Appendix A rules A2-A6) into the A (up to the dump) or B sums.
+struct SampleCtx {
+  uint32_t cph0, kph0, cinc, kinc, hc0, w1, stale_idx;
+  const uint8_t *tile;
+  const uint32_t *tbl;
+  const uint2 *lut;
+  int fmt;
+};
+__device__ __forceinline__ void eval_sample(const SampleCtx &c, int i, int (&sumA)[6], int (&sumB)[6], bool &anyB) {
+  const unsigned long long ki = (unsigned long long)c.kph0 + (unsigned long long)i * c.kinc;
+  const uint32_t wb = (uint32_t)(ki >> 32);
+  const bool inA = wb < c.w1;
+  const uint32_t rel = wb - c.w1;
+  const uint32_t hh = inA ? c.hc0 + wb : (rel == 0 ? c.stale_idx : rel);
+  const uint32_t t = c.tbl[hh];
+  int I, Q;
+  load_sample(c.tile, c.fmt, i, I, Q);
+  const uint2 ab = c.lut[(c.cph0 + (uint32_t)i * c.cinc) >> 29];
+  const int v = I * (int)ab.x + Q * (int)ab.y;
+  int vi, vq;
+  unpack_lanes(v, vi, vq);
+  const int cE = sext8(t, 0), cP = sext8(t, 1), cL = sext8(t, 2);
+  if (inA) {
+    sumA[0] += cL * vi; sumA[1] += cL * vq; sumA[2] += cP * vi;
+    sumA[3] += cP * vq; sumA[4] += cE * vi; sumA[5] += cE * vq;
+  } else {
+    sumB[0] += cL * vi; sumB[1] += cL * vq; sumB[2] += cP * vi;
+    sumB[3] += cP * vq; sumB[4] += cE * vi; sumB[5] += cE * vq;
+    anyB = true;
+  }
+}
+
+// One block on the segment path, one correlator thread of NT.  Threads 0..NT-2 own the full segments
+// 1 + tid*H ... ; a thread whose run contains the dump keeps the part before it and hands the rest to thread NT-1
+// (which has no segments of its own), so every thread's sums belong to one side of the dump.  Warp 0 evaluates the
+// head segment and whatever follows the owned segments (the tail) one sample per lane.
+template <int NT, int H>
+__device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx &sc, const uint32_t tile_addr, const uint32_t tbl_addr,
+                                          const uint32_t alias_addr, const uint32_t vlut_lane, const PipeK K, const int nsamp,
+                                          const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB) {
+  // Which run of segments a thread owns: consecutive runs start 43 bytes apart in the tile (H = 11), i.e. lanes l and
+  // l+3 of a warp would read the same bank (4-way conflicts on the two window loads of every segment); stepping
+  // through the runs with stride 7 spreads a warp over the banks (2-way).
+  constexpr int STEP = NT == 96 ? 7 : 1;
+  const int tid = (ptid * STEP) % NT;
+  const uint32_t wtot = p.wtot, w1 = p.w1;
+  const uint32_t NF = wtot > 0 ? wtot - 1 : 0;  // full segments: 1 .. NF
+  constexpr uint32_t OWNED = (uint32_t)(NT - 1) * H;
+  const double nk05 = -(double)p.kph0 - 0.5;
+  uint32_t m0, nv;
+  if (tid < NT - 1) {
+    const uint32_t first = (uint32_t)tid * H;
+    m0 = 1 + first;
+    nv = NF > first ? min(NF - first, (uint32_t)H) : 0u;
+    if (m0 < w1 && w1 < m0 + nv) nv = w1 - m0;  // the run contains the dump: keep the part before it
+  } else {
+    // the part after the dump of the thread whose run contains it
+    m0 = 1;
+    nv = 0;
+    if (w1 >= 2) {
+      const uint32_t ts = (w1 - 2) / H, first = ts * H;
+      const uint32_t end = 1 + first + (NF > first ? min(NF - first, (uint32_t)H) : 0u);
+      if (ts < (uint32_t)(NT - 1) && w1 < end) {
+        m0 = w1;
+        nv = end - w1;
+      }
+    }
+  }
+  if (nv == 0) m0 = 1;  // idle: every address stays in bounds
+  const bool clsB = m0 >= w1;
+  uint32_t hp;
+  if (clsB) {
+    const uint32_t rel = m0 - w1;  // first half chip after the dump: stale bits, then tbl[1], tbl[2], ... (rule A6)
+    hp = rel == 0 ? alias_addr : tbl_addr + 4u * rel;
+  } else
+    hp = tbl_addr + 4u * (p.hc0 + m0);
+  const uint32_t s = seg_start(m0, nk05, p.dinv);
+  int pE, pP, pL;
+  correlate_segments<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 7u * p.kinc, hp, (int)nv,
+                        vlut_lane, K, pE, pP, pL);
+  {
+    int v[6];
+    unpack_lanes(pL, v[0], v[1]);
+    unpack_lanes(pP, v[2], v[3]);
+    unpack_lanes(pE, v[4], v[5]);
+    if (clsB) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) sumB[q] += v[q];
+      anyB |= nv != 0;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 6; q++) sumA[q] += v[q];
+    }
+  }
+  if (ptid < 32) {
+    // head: segment 0 = samples before the first wrap; tail: from the first segment nobody owns to the block end
+    const uint32_t head_end = wtot == 0 ? (uint32_t)nsamp : min(seg_start(1, nk05, p.dinv), (uint32_t)nsamp);
+    const uint32_t mt = 1 + min(NF, OWNED);
+    const uint32_t tail_start = mt > wtot ? (uint32_t)nsamp : min(seg_start(mt, nk05, p.dinv), (uint32_t)nsamp);
+    const uint32_t total = head_end + ((uint32_t)nsamp - tail_start);
+    for (uint32_t e = (uint32_t)ptid; e < total; e += 32) {
+      const uint32_t i = e < head_end ? e : tail_start + (e - head_end);
+      eval_sample(sc, (int)i, sumA, sumB, anyB);
+    }
+  }
+}
+
+// a block whose code NCO does not fit the segment form: every sample from the closed forms, NT lanes
+template <int NT>
+__device__ __forceinline__ void generic_block(const SampleCtx &sc, const int nsamp, const int tid, int (&sumA)[6], int (&sumB)[6],
+                                              bool &anyB) {
+  for (int i = tid; i < nsamp; i += NT) eval_sample(sc, i, sumA, sumB, anyB);
+}

@@ -1,6 +1,7 @@
 // track_ws.cuh -- track_ws_kernel: the warp-specialised channel loop (the hot path) and its (channel, slice) work queue.
 #pragma once
 #include "track_common.cuh"
+#include "track_seg.cuh"
 
 // ==================================================================================================
 // Warp-specialised variant of the channel loop (the hot path for 8192-sample TMA-staged blocks).
@@ -18,12 +19,6 @@
 //                   barrier in the loop; a warp is at most one block ahead of the slowest one.
 //
 // Same arithmetic, same rules, same results as track_loop_kernel (which remains the generic variant).
-struct __align__(16) BlockParams {
-  uint32_t cph0, kph0, cinc, kinc;
-  uint32_t hc0, w1, stale_idx, stale_bits;
-  int mode, event, pad0, pad1;
-};
-
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -110,14 +105,22 @@ __device__ __forceinline__ void copy_in_cg(T &dst, const T *src) {  // L2-cohere
   for (int i = 0; i < (int)(sizeof(T) / 4); i++) d4[i] = __ldcg(s4 + i);
 }
 
-// SPT samples per correlator thread: 32 (256 correlator threads, shortest block latency) or 64 (128
-// threads: half the per-block overhead instructions and six resident CTAs per SM for dense grids).
-template <int MINB, int FMT, int SPT>
-__global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const TrackArgs a, const int tile_bytes) {
-  constexpr int WS_CORR_THREADS = 8192 / SPT;
+// Correlator side, two forms:
+//   SEGH == 0  8192/CT consecutive samples per correlator thread: 32 (CT = 256, shortest block latency) or 64 (CT =
+//              128: half the per-block overhead instructions, more resident CTAs per SM).  Any code NCO rate
+//              with 4*kinc < 2^32, both sample formats.
+//   SEGH  > 0  SEGH consecutive half-chip segments per correlator thread (track_seg.cuh), CT correlator
+//              threads: packed input, code NCO rates with 7 or 8 samples per half chip (the GPS C/A code at the
+//              front end's 16 Msps); blocks with another rate are evaluated sample by sample from the closed forms.
+template <int MINB, int FMT, int CT, int SEGH = 0>
+__global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs a, const int tile_bytes) {
+  constexpr int WS_CORR_THREADS = CT;
+  constexpr int SPT = SEGH > 0 ? 32 : 8192 / CT;  // samples per correlator thread of the fixed-run form
+  static_assert(SEGH > 0 || CT * SPT == 8192, "fixed-run form: CT threads x SPT samples cover the largest block");
   constexpr int WS_THREADS = WS_CORR_THREADS + 32;
   constexpr int fmt = FMT;
   constexpr bool packed_native = FMT == GNSSB200_FMT_PACKED2;
+  static_assert(SEGH == 0 || FMT == GNSSB200_FMT_PACKED2, "the segment form reads packed samples");
   __shared__ ChanShared cs;
   __shared__ BlockParams params[2];
   __shared__ uint2 lut[8];
@@ -126,7 +129,11 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   __shared__ __align__(16) int totals[12];
   __shared__ __align__(8) uint64_t dfull[2], pfull[2], empty[2], tfull;
   extern __shared__ __align__(128) uint8_t tiles[];
-  uint32_t *vlut = reinterpret_cast<uint32_t *>(tiles + 2 * (size_t)tile_bytes);
+  // mixer table behind the two tiles; the segment form ORs the sample code into the table address, so there the
+  // table starts on a 2048-byte boundary of the shared window (the launch reserves the slack)
+  uint8_t *vlut_raw = tiles + 2 * (size_t)tile_bytes;
+  if (SEGH > 0) vlut_raw += (2048u - (smem_u32(vlut_raw) & 2047u)) & 2047u;
+  uint32_t *vlut = reinterpret_cast<uint32_t *>(vlut_raw);
 
   __shared__ int s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,11 +231,25 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
   // ---------------- control lane ----------------
   if (warp == WS_CORR_THREADS / 32) {
     if (lane != 0) return;
+    uint32_t inv_of = 0;  // code NCO increment `dinv` belongs to
+    double dinv = 0.0;
     auto publish = [&](int slot, const StepParams &sp, bool event) {
       BlockParams &p = params[slot];
       p.cph0 = sp.cph0; p.kph0 = sp.kph0; p.cinc = sp.cinc; p.kinc = sp.kinc;
       p.hc0 = sp.hc0; p.w1 = sp.w1; p.stale_idx = sp.stale_idx; p.stale_bits = sp.stale_bits;
       p.mode = sp.mode; p.event = event ? 1 : 0;
+      if constexpr (SEGH > 0) {
+        if (sp.mode == MODE_FAST) {
+          const bool ok = seg_kinc_ok(sp.kinc);
+          if (ok && sp.kinc != inv_of) {  // the division only when the code NCO word changed
+            dinv = 1.0 / (double)sp.kinc;
+            inv_of = sp.kinc;
+          }
+          p.wtot = (uint32_t)(((unsigned long long)sp.kph0 + (unsigned long long)a.nsamp * sp.kinc) >> 32);
+          p.seg = ok ? 1u : 0u;
+          p.dinv = dinv;
+        }
+      }
       alias_tbl[slot][0] = sp.stale_bits;
       mbar_arrive(&pfull[slot]);  // release: the stores above are visible to whoever observes the phase
     };
@@ -421,7 +442,21 @@ __global__ void __launch_bounds__(8192 / SPT + 32, MINB) track_ws_kernel(const T
       CP(t_dw)
       int sumA[6] = {0, 0, 0, 0, 0, 0}, sumB[6] = {0, 0, 0, 0, 0, 0};
       bool anyB = false;
-      {
+      if constexpr (SEGH > 0) {
+        BlockParams bp;
+        bp.cph0 = cph0; bp.kph0 = kph0; bp.cinc = cinc; bp.kinc = kinc;
+        bp.hc0 = hc0; bp.w1 = w1; bp.stale_idx = stale_idx; bp.stale_bits = stale_bits;
+        const uint2 p3 = reinterpret_cast<const uint2 *>(&params[slot])[5];
+        bp.wtot = p3.x;
+        bp.seg = p3.y;
+        bp.dinv = params[slot].dinv;
+        const SampleCtx sc{cph0, kph0, cinc, kinc, hc0, w1, stale_idx, tile, tbl, lut, fmt};
+        if (bp.seg)
+          seg_block<CT, SEGH>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
+                              PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, tid, sumA, sumB, anyB);
+        else
+          generic_block<CT>(sc, a.nsamp, tid, sumA, sumB, anyB);
+      } else {
         uint32_t cur[SPT / 2];
         uint32_t pk[SPT / 8];
         if (live && packed_native) {

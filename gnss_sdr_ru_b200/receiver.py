@@ -174,6 +174,11 @@ class TrackingEngine:
         """blocks per work-queue slice of the tracking kernel (0 = automatic); results do not depend on it"""
         check(self.L.gnssb200_set_track_slice(self.h, blocks), "gnssb200_set_track_slice")
 
+    def set_track_variant(self, form: int = 0, occ: int = 0):
+        """kernel form (0 auto, 1 barrier kernel, 2 fixed sample runs, 3/4/5 half-chip segments x 96/192/384 threads) and
+        occupancy variant (0 auto); results do not depend on it"""
+        check(self.L.gnssb200_set_track_variant(self.h, form, occ), "gnssb200_set_track_variant")
+
     def launch_count(self) -> int:
         return int(self.L.gnssb200_launch_count(self.h))
 

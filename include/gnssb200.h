@@ -208,6 +208,12 @@ int gnssb200_acq_serial(gnssb200_handle *h, const void *d_if, int fmt, int64_t n
  * not depend on it. */
 int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks);
 
+/* Which form of the tracking kernel runs (results do not depend on it; tests and A/B measurements use it).
+ * form: 0 automatic; 1 the barrier-synchronised kernel; 2 warp-specialised, fixed runs of 32 / 64 samples per
+ * thread; 3 / 4 / 5 warp-specialised, half-chip segments with 96 / 192 / 384 correlator threads (packed input).
+ * occ: 0 automatic, else the resident-CTAs-per-SM variant (2..6) that would be chosen for that many channels per SM. */
+int gnssb200_set_track_variant(gnssb200_handle *h, int form, int occ);
+
 /* Host-buffer pipeline of gnssb200_track_run_host: blocks per stream and staging chunk (0 = automatic, about 384
  * blocks, at least 32 MiB per chunk); results do not depend on it.  The dump records of a multi-chunk run are read
  * back window by window while later chunks are still running when h_dumps is pinned (or registered) host memory;

@@ -46,11 +46,12 @@ def _setup_pair(oracle_lib, n_streams=1, cfg_over=None):
     return eng, orcs
 
 
-def _compare_run(eng, orcs, recs, nblk, fmt=abi.FMT_INT8_IQ, packed=None, cap=4000):
-    dumps, cnt = eng.run_host(packed if packed is not None else recs, nblk, NS, fmt, dump_cap=cap)
+def _compare_run(eng, orcs, recs, nblk, fmt=abi.FMT_INT8_IQ, packed=None, cap=4000, ns=None):
+    ns = NS if ns is None else ns
+    dumps, cnt = eng.run_host(packed if packed is not None else recs, nblk, ns, fmt, dump_cap=cap)
     eng.download()
     for s, o in enumerate(orcs):
-        n, odumps, ocnt = o.run(recs[s], NS, nblk, dump_cap=cap)
+        n, odumps, ocnt = o.run(recs[s], ns, nblk, dump_cap=cap)
         assert n == nblk
         assert np.array_equal(cnt[s], ocnt), (cnt[s], ocnt)
         for ch in range(12):
@@ -101,6 +102,46 @@ def test_closed_loop_packed2(oracle_lib, track_record):
     eng, orcs = _setup_pair(oracle_lib)
     sub = rec[: 2 * NS * n]
     _compare_run(eng, orcs, sub[None, :], n, fmt=abi.FMT_PACKED2, packed=pack2(sub)[None, :])
+
+
+# (form, occ, block length): every form of the tracking kernel (gnssb200_set_track_variant) on packed input, including
+# block lengths that are not a multiple of 64 samples (4000, 8160: the 64-samples-per-thread variants must not be
+# picked there) and the shortest TMA-staged blocks
+KERNEL_FORMS = [(0, 0, 8192), (1, 0, 8192), (2, 0, 8192), (2, 3, 8192), (2, 4, 8192), (2, 5, 8192), (2, 6, 8192), (2, 4, 4000),
+                (2, 5, 8160), (3, 0, 8192), (3, 5, 8192), (3, 6, 8192), (3, 6, 4000), (3, 4, 8160), (4, 0, 8192), (4, 0, 4000),
+                (5, 0, 8192), (5, 0, 8160), (3, 0, 32)]
+
+
+@pytest.mark.parametrize("form,occ,ns", KERNEL_FORMS)
+def test_packed_kernel_forms(oracle_lib, track_record, form, occ, ns):
+    """Search (code slews, false alarms at a low threshold), confirm, pull-in, tracking and TIC latches on packed
+    2+2-bit input, three streams, through each kernel form: every dump record and the final receiver state equal
+    the oracle's."""
+    from gnss_sdr_ru_b200.synth import pack2
+
+    rec, _ = track_record
+    nblk = 420 if ns >= 4000 else 3000
+    S = 3
+    over = dict(tic_period=0.0123, acq_thresh=1100)
+    recs = np.stack([np.roll(rec[: 2 * ns * nblk], 2 * 1013 * s) for s in range(S)])
+    eng, orcs = _setup_pair(oracle_lib, n_streams=S, cfg_over=over)
+    eng.set_track_variant(form, occ)
+    _compare_run(eng, orcs, recs, nblk, fmt=abi.FMT_PACKED2, packed=np.stack([pack2(r) for r in recs]), cap=1200, ns=ns)
+
+
+def test_segment_form_other_code_rates(oracle_lib, track_record):
+    """The half-chip-segment kernel with code NCO words outside its 7-or-8-samples range (twice and 0.9 times the
+    C/A rate on some channels, set through the configuration and through per-channel register writes): those blocks
+    are evaluated from the closed forms inside the same kernel; results equal the oracle's."""
+    from gnss_sdr_ru_b200.synth import pack2
+
+    rec, _ = track_record
+    nblk = 300
+    sub = rec[: 2 * NS * nblk]
+    for over in (dict(gps_code_f=0.9 * 1023000.0), dict(gps_code_f=1023000.0 * 1.1171), dict(gps_code_f=1023000.0 * 0.9776)):
+        eng, orcs = _setup_pair(oracle_lib, cfg_over=over)
+        eng.set_track_variant(3, 0)
+        _compare_run(eng, orcs, sub[None, :], nblk, fmt=abi.FMT_PACKED2, packed=pack2(sub)[None, :])
 
 
 def test_closed_loop_multi_stream(oracle_lib, track_record):
