@@ -225,6 +225,8 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 96, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 96, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 192, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 192, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 192, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       if (h->device >= 0 && h->device < 64) aws[h->device] = true;
     }
@@ -282,6 +284,10 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (seg && (form == 5 || (form == 0 && per_sm <= 1)))
       track_ws_kernel<2, GNSSB200_FMT_PACKED2, 384, 3><<<items, 416, dyn_seg, st>>>(a, tile_bytes);
+    else if (seg && form == 4 && per_sm >= 6)
+      track_ws_kernel<6, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
+    else if (seg && form == 4 && per_sm >= 4)
+      track_ws_kernel<5, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
     else if (seg && (form == 4 || (form == 0 && per_sm <= 2)))
       track_ws_kernel<3, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
     else if (seg && per_sm >= 6)
