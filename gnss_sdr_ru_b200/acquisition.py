@@ -137,6 +137,43 @@ class AcquisitionEngine:
         amb = self.L.gnssb200_acq_finalize(C.byref(c), r.ctypes.data, res)
         return res, amb
 
+    def acquisition_distributed(self, d_iq_ptr: int, n_samples: int, settings: Settings, fmt: int = abi.FMT_INT8_IQ, group=None,
+                                return_rows=False):
+        """acquisition() with the (sv, Doppler bin) grid sharded over the ranks of a torch.distributed group (one
+        process per GPU, the record resident on every GPU): this rank searches rows r % world == rank, one all-gather
+        of the 16-byte row tables (NCCL when the group is an NCCL group), then every rank runs the same peak /
+        second-peak / threshold logic on the merged table.  Returns the same dict as acquisition() on every rank."""
+        import torch
+        import torch.distributed as dist
+
+        from .partition import merge_row_tables
+
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        nb = self.num_bins(settings)
+        n_sv = len(settings.acqSatelliteList)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rows = torch.zeros(n_sv * nb * abi.ACQ_ROW_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.search_device(d_iq_ptr, n_samples, settings, rows.data_ptr(), fmt=fmt, part_index=rank, part_count=world,
+                           stream=torch.cuda.current_stream().cuda_stream)
+        gathered = torch.empty(world * rows.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, rows, group=group)
+        merged = merge_row_tables(gathered.cpu().numpy().view(abi.ACQ_ROW_DTYPE).reshape(world, n_sv * nb))
+        res, _ = self.finalize(settings, merged)
+        out = dict(
+            carrFreq=np.array([r.carrFreq for r in res]),
+            codePhase=np.array([r.codePhase for r in res]),
+            peakMetric=np.array([r.peakMetric for r in res]),
+            freqChannel=np.array([r.sv for r in res]),
+            bin=np.array([r.bin for r in res]),
+            codePhaseRaw=np.array([r.codePhaseRaw for r in res]),
+            peak=np.array([r.peak for r in res]),
+            second=np.array([r.second for r in res]),
+        )
+        if return_rows:
+            out["rows"] = merged.reshape(n_sv, nb)
+        return out
+
     def last_kernel_ms(self) -> float:
         return float(self.L.gnssb200_last_kernel_ms(self.h))
 

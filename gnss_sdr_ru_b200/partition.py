@@ -32,6 +32,23 @@ def merge_row_tables(gathered: np.ndarray) -> np.ndarray:
     return merged
 
 
+def prns_of_rank(prn_list, rank: int, world: int) -> list:
+    """Serial-search cell map: the sweep of one PRN over its Doppler bins is one sequential run
+    of one correlator channel (the NCO phases carry over from bin to bin, quirk Q6), so the PRN is the unit that
+    shards: entry i of the list is searched by rank i % world."""
+    return [p for i, p in enumerate(prn_list) if i % world == rank]
+
+
+def merge_cell_maps(gathered_cells: np.ndarray, gathered_counts: np.ndarray, prn_list, world: int) -> dict:
+    """gathered_cells: (world, per_rank, cells_cap) gnssb200_serial_cell, gathered_counts: (world, per_rank); rank r's slot
+    j holds entry r + j*world of prn_list.  Returns {prn: cells} in the order of prn_list."""
+    out = {}
+    for i, p in enumerate(prn_list):
+        r, j = i % world, i // world
+        out[int(p)] = gathered_cells[r, j, : gathered_counts[r, j]].copy()
+    return out
+
+
 def all_gather_rows(rows_tensor, world: int):
     """torch.distributed all-gather of a device (NCCL) or host (gloo) uint8 row table."""
     import torch

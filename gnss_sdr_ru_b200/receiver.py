@@ -199,6 +199,36 @@ def acq_serial(handle, d_if_ptr: int, fmt: int, n_samples: int, prn_list, search
     return {int(p): cells[i, : n[i]].copy() for i, p in enumerate(prn)}
 
 
+def acq_serial_distributed(handle, d_if_ptr: int, fmt: int, n_samples: int, prn_list, search_max_f: int = 5, max_prn_delay: int = 2045,
+                           cells_cap: int = 4096, group=None):
+    """acq_serial with the PRN list sharded over the ranks of a torch.distributed group (entry i on rank i % world, the
+    record resident on every GPU) and one all-gather of the cell tables; every rank returns the complete map."""
+    import torch
+    import torch.distributed as dist
+
+    from .partition import merge_cell_maps, prns_of_rank
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = prns_of_rank(list(prn_list), rank, world)
+    per_rank = (len(prn_list) + world - 1) // world
+    cells = np.zeros((per_rank, cells_cap), dtype=abi.SERIAL_CELL_DTYPE)
+    n = np.zeros(per_rank, dtype=np.int32)
+    if mine:
+        got = acq_serial(handle, d_if_ptr, fmt, n_samples, mine, search_max_f, max_prn_delay, cells_cap)
+        for j, p in enumerate(mine):
+            n[j] = len(got[p])
+            cells[j, : n[j]] = got[p]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t_cells = torch.from_numpy(cells.view(np.uint8).reshape(-1)).to(dev)
+    t_n = torch.from_numpy(n).to(dev)
+    g_cells = torch.empty(world * t_cells.numel(), dtype=torch.uint8, device=dev)
+    g_n = torch.empty(world * per_rank, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(g_cells, t_cells, group=group)
+    dist.all_gather_into_tensor(g_n, t_n, group=group)
+    gc = g_cells.cpu().numpy().view(abi.SERIAL_CELL_DTYPE).reshape(world, per_rank, cells_cap)
+    return merge_cell_maps(gc, g_n.cpu().numpy().reshape(world, per_rank), list(prn_list), world)
+
+
 def serial_search_cell_map(dumps: np.ndarray, counts: np.ndarray):
     """Turn the dump records of a run with the detection threshold out of reach into the GP2021-semantics
     search cell map {(stream, channel): array of (n_freq, code delay in half chips, IP, QP, rss)}.

@@ -143,6 +143,13 @@ def exclusion_range(s: AcqSettings, codePhase1: int) -> np.ndarray:
     return rng
 
 
+def acquisition_job(job):
+    """(int8 I,Q record, settings) -> acquisition(): a picklable entry point so that tests can run one code entry per
+    process (BASELINE config 4 needs about two minutes per PRN in this formulation)."""
+    rec, s = job
+    return acquisition(to_complex(rec), s)
+
+
 def acquisition(longSignal: np.ndarray, s: AcqSettings):
     """acqResults = acquisition(longSignal, settings).  Returns a list of dicts (one per sv) with
     the reference's fields plus the raw peak data."""

@@ -187,21 +187,53 @@ def test_c3_half_grid_vs_oracle(oracle_lib):
     _check(res, ora, res["rows"], 121)
 
 
-def test_c4_full_size_finds_the_generated_satellites():
-    """BASELINE config 4 at full size (32 PRN x 401 bins, 10 ms x 20 non-coherent, 205 M cells): a
-    size-independent property instead of the (hours-long) float64 oracle -- every satellite the
-    generator put into the record at >= 33 dB-Hz is detected at its true Doppler bin and code phase."""
+def test_c4_full_size_vs_oracle(oracle_lib):
+    """BASELINE config 4 at its own settings and signal levels (10 ms coherent x 20 non-coherent, 401 bins of 50 Hz,
+    satellites at 28-33 dB-Hz as generated) against the float64 restatement in the reference's formulation
+    (160000-point FFTs, one wipe-off + FFT per bin and block): the weakest satellite of the record (PRN 32,
+    28.2 dB-Hz), one at 31.2 dB-Hz and a PRN that is not in the record -- Doppler bin and code phase exact, peak and
+    peakMetric within 1e-4, every one of the 401 row maxima within 1e-4.  One process per PRN (about two minutes each)."""
+    import multiprocessing as mp
+
+    from oracle import pcps_oracle as po
     from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
     from gnss_sdr_ru_b200.scenarios import gps_weak_acq_scenario
     from gnss_sdr_ru_b200.synth import make_record
 
     sats = gps_weak_acq_scenario(4004)
-    for s in sats:
-        s.cn0_dbhz = max(s.cn0_dbhz, 36.0)
+    assert min(s.cn0_dbhz for s in sats) < 29.0 and sum(s.cn0_dbhz <= 33.0 for s in sats) == 4
+    rec = make_record(sats, 16000 * 200, seed=4004)
+    svs = [32, 22, 5]
+    assert {32, 22} <= {s.prn for s in sats} and 5 not in {s.prn for s in sats}
+    jobs = [(rec, po.AcqSettings.gps(acqSearchBand=20.0, acqCohIntegration=10, n_noncoh=20, svList=[sv])) for sv in svs]
+    with mp.get_context("spawn").Pool(len(svs)) as pool:
+        pending = pool.map_async(po.acquisition_job, jobs)
+        st = Settings.gps(acqSearchBand=20.0, acqCohIntegration=10, n_noncoh=20, acqSatelliteList=svs)
+        eng = AcquisitionEngine()
+        assert eng.num_bins(st) == 401
+        res = eng.acquisition(rec, st, return_rows=True)
+        ora = [r[0] for r in pending.get(timeout=1500)]
+    _check(res, ora, res["rows"], 401)
+    # what the threshold makes of them is part of the result: same decision on both sides
+    assert [int(x) for x in res["freqChannel"]] == [o["freqChannel"] for o in ora]
+    assert int(res["freqChannel"][1]) == 22 and int(res["freqChannel"][2]) == 0
+
+
+def test_c4_full_size_finds_the_generated_satellites():
+    """BASELINE config 4 at full size (32 PRN x 401 bins, 10 ms x 20 non-coherent, 205 M cells), all 32 PRNs: a
+    size-independent property beside the oracle comparison above -- every satellite the generator put into the
+    record at >= 31 dB-Hz is detected at its true Doppler bin and code phase, no absent PRN is reported."""
+    from gnss_sdr_ru_b200.acquisition import AcquisitionEngine, Settings
+    from gnss_sdr_ru_b200.scenarios import gps_weak_acq_scenario
+    from gnss_sdr_ru_b200.synth import make_record
+
+    sats = gps_weak_acq_scenario(4004)  # signal levels as BASELINE config 4 states them: 28-33 dB-Hz and two at 45
     rec = make_record(sats, 16000 * 200, seed=4004)
     st = Settings.gps(acqSearchBand=20.0, acqCohIntegration=10, n_noncoh=20)
     res = AcquisitionEngine().acquisition(rec, st)
     for s in sats:
+        if s.cn0_dbhz < 31.0:  # 200 ms without data-bit handling does not lift these over the threshold of 3 (the float64
+            continue           # restatement agrees: test_c4_full_size_vs_oracle compares PRN 32 at 28.2 dB-Hz)
         i = s.prn - 1
         assert int(res["freqChannel"][i]) == s.prn, (s.prn, res["peakMetric"][i])
         assert abs(res["carrFreq"][i] - (2.42e6 + s.doppler_hz)) <= 50.0

@@ -17,7 +17,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from gnss_sdr_ru_b200 import abi
-    from gnss_sdr_ru_b200.partition import all_gather_rows, merge_row_tables, row_owner, streams_of_rank
+    from gnss_sdr_ru_b200.partition import all_gather_rows, merge_cell_maps, merge_row_tables, prns_of_rank, row_owner, streams_of_rank
 
     g = np.load(os.path.join(ROOT, "tests", "golden", "acq_golden.npz"))
     rows_full = g["rows"]  # (sv, bin, [peak, arg, blk]) from the float64 oracle
@@ -43,6 +43,24 @@ def _worker(rank, world, port, q):
     cnt[owned] = 1
     dist.all_reduce(cnt)
     ok = ok and bool((cnt == 1).all())
+    # serial-search cell map: PRN i of the list on rank i % world, gathered tables merged back in list order
+    prns = [27, 9, 32, 1, 5]
+    mine = prns_of_rank(prns, rank, world)
+    per_rank, cap = (len(prns) + world - 1) // world, 7
+    cells = np.zeros((per_rank, cap), dtype=abi.SERIAL_CELL_DTYPE)
+    cnt_c = np.zeros(per_rank, dtype=np.int32)
+    for j, p in enumerate(mine):
+        cnt_c[j] = 1 + p % 5
+        cells["prn"][j, : cnt_c[j]] = p
+        cells["codes"][j, : cnt_c[j]] = np.arange(cnt_c[j])
+    tc = torch.from_numpy(cells.view(np.uint8).reshape(-1).copy())
+    gc = torch.empty(world * tc.numel(), dtype=torch.uint8)
+    dist.all_gather_into_tensor(gc, tc)
+    tn = torch.from_numpy(cnt_c)
+    gn = torch.empty(world * per_rank, dtype=torch.int32)
+    dist.all_gather_into_tensor(gn, tn)
+    cm = merge_cell_maps(gc.numpy().view(abi.SERIAL_CELL_DTYPE).reshape(world, per_rank, cap), gn.numpy().reshape(world, per_rank), prns, world)
+    ok = ok and list(cm) == prns and all(len(cm[p]) == 1 + p % 5 and (cm[p]["prn"] == p).all() for p in prns)
     # max-over-ranks timing reduction used by bench.py
     tmax = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -144,6 +144,44 @@ def test_segment_form_other_code_rates(oracle_lib, track_record):
         _compare_run(eng, orcs, sub[None, :], nblk, fmt=abi.FMT_PACKED2, packed=pack2(sub)[None, :])
 
 
+def test_int8_real_samples_vs_reference(oracle_lib, track_record):
+    """GNSSB200_FMT_INT8_I: real (I-only) int8 samples, the reference's `use_iq_processing = 0` branch
+    (OSG/correlator/correlator.c:217-224), against the compiled reference itself with that global cleared:
+    closed loop, every dump record."""
+    if not oracle_lib.have_ref():
+        pytest.skip("needs oracle/_ref (the reference compiled in place)")
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+
+    rec, _ = track_record
+    nblk, cap = 500, 700
+    real = np.ascontiguousarray(rec[: 2 * NS * nblk : 2])  # the I samples as a real record
+    ref = oracle_lib.RefReceiver()
+    try:
+        ref.use_iq.value = 0
+        ref.cold_allocate(PRNS)
+        for ch, nf in WARM:
+            ref.warm_start(ch, nf)
+        # the native driver steps 2*nsamp bytes per block; the I-only branch reads the first nsamp of them
+        slots = np.zeros((nblk, 2 * NS), dtype=np.int8)
+        slots[:, :NS] = real.reshape(nblk, NS)
+        n, od, oc = ref.run(slots.reshape(-1), NS, nblk, dump_cap=cap)
+    finally:
+        ref.use_iq.value = 1
+    assert n == nblk
+    for form in (0, 1):
+        eng = TrackingEngine(n_streams=1)
+        eng.simple_cold_allocate(0, PRNS)
+        for ch, nf in WARM:
+            eng.warm_start(0, ch, nf)
+        eng.upload()
+        eng.set_track_variant(form, 0)
+        dumps, cnt = eng.run_host(real[None, :], nblk, NS, abi.FMT_INT8_I, dump_cap=cap)
+        assert np.array_equal(cnt[0], oc), (cnt[0], oc)
+        for ch in range(12):
+            assert np.array_equal(dumps[0, ch, : oc[ch]], od[ch, : oc[ch]]), f"form {form} channel {ch}"
+        assert oc.sum() > 1400 and len(set(int(x) for x in dumps[0, 0, : oc[0]]["state"])) >= 2
+
+
 def test_closed_loop_multi_stream(oracle_lib, track_record):
     rec, _ = track_record
     n, S = 250, 5
