@@ -100,6 +100,24 @@ extern "C" int gnssb200_isr_math_eval(gnssb200_handle *h, int n, const int32_t *
   return 0;
 }
 
+// TRACK_CHECK builds: violations counted by the kernels since the last call (-1: the library was built without the checks)
+extern "C" int gnssb200_track_check_failures(unsigned out[8]) {
+#ifdef TRACK_CHECK
+  unsigned h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(h, g_track_check_fail, sizeof h) != cudaSuccess) return -2;
+  cudaMemcpyToSymbol(g_track_check_fail, z, sizeof z);
+  int n = 0;
+  for (int i = 0; i < 8; i++) {
+    if (out) out[i] = h[i];
+    n += (int)h[i];
+  }
+  return n;
+#else
+  (void)out;
+  return -1;
+#endif
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 void build_code_table_host(uint32_t *table) {
   // C/A Gold codes, G2 register start states per PRN (IS-GPS-200; same values as correlator.c:67-71),

@@ -5,6 +5,16 @@
 #include "isr_device.cuh"
 
 
+// -DTRACK_CHECK: every shared-memory address the correlator warps form and every queue / ring invariant is checked on
+// the device; violations are counted in g_track_check_fail (read through gnssb200_track_check_failures).  This pool
+// has compute-sanitizer closed, so this build is what the address / hand-over evidence in profiles/ comes from.
+__device__ unsigned g_track_check_fail[8];
+#ifdef TRACK_CHECK
+#define TCHECK(slot, cond) do { if (!(cond)) atomicAdd(&g_track_check_fail[slot], 1u); } while (0)
+#else
+#define TCHECK(slot, cond) do { } while (0)
+#endif
+
 #define MODE_STOP (-1)
 #define MODE_IDLE 0
 #define MODE_FAST 1

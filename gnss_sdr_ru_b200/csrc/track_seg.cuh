@@ -50,11 +50,16 @@ __device__ __forceinline__ uint32_t seg_start(uint32_t m, double nk05 /* -kph0 -
 // address of the tile + 4*s), cph / ks = carrier / code NCO phase at s (ks < kinc), hp = shared-memory byte address
 // of the first segment's code-table entry (consecutive entries follow), nvalid = segments that count.
 // Sums come back as two 16-bit lanes (ival + 65536*qval), |lane| <= 8*H*9.
+struct SegBounds {  // shared-memory windows the loop may touch (TRACK_CHECK builds)
+  uint32_t tile_lo, tile_hi, bits_lo, bits_hi, vlut_lo, vlut_hi;
+};
 template <int H>
 __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uint32_t ks, const uint32_t cinc, const uint32_t kinc,
                                                    const uint32_t k7, const uint32_t hp, const int nvalid, const uint32_t vlut_lane,
-                                                   const PipeK K, int &accE, int &accP, int &accL) {
+                                                   const PipeK K, int &accE, int &accP, int &accL, const SegBounds bnd) {
   int aE = 0, aP = 0, aL = 0;
+  TCHECK(0, ks < kinc || nvalid == 0);                            // a run starts on a code-NCO wrap
+  TCHECK(1, hp >= bnd.bits_lo && hp + 4u * H <= bnd.bits_hi);     // code-table entries of the run
   // Rolled on purpose: the body is ~75 instructions; unrolled H times every warp streams through > 10 KB of code per
   // block and the warps of an SM, each somewhere else in it, keep missing the instruction cache (ncu: a sixth of the
   // stalled warp-cycles were `no_instructions`).
@@ -63,6 +68,7 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
   for (int j = 0; j < H; j++) {
     // eight 4-bit sample codes from bit address q (two aligned words, funnel shift by q mod 32)
     const uint32_t a = (q >> 3) & ~3u;
+    TCHECK(2, a >= bnd.tile_lo && a + 8u <= bnd.tile_hi);  // sample window inside the tile (+ read-ahead slack)
     const uint32_t lo = lds_u32(a), hi = lds_u32(a + 4);
     const uint32_t wd = __funnelshift_r(lo, hi, q);
     // 7 or 8 samples: the segment ends with the sample whose code step wraps
@@ -86,6 +92,7 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
       uint32_t ca;
       asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(ca) : "r"(sh), "r"(vlut_lane));  // (sh & 0x780) | vlut_lane
       const uint32_t idx = __umulhi(cph, K.k8);
+      TCHECK(3, idx * K.k2048 + ca >= bnd.vlut_lo && idx * K.k2048 + ca + 4u <= bnd.vlut_hi);  // mixer table entry
       v[k] = (int)lds_u32(idx * K.k2048 + ca);
       if (k < 7) cph = cinc * K.k1 + cph;
     }
@@ -120,6 +127,7 @@ __device__ __forceinline__ void eval_sample(const SampleCtx &c, int i, int (&sum
   const bool inA = wb < c.w1;
   const uint32_t rel = wb - c.w1;
   const uint32_t hh = inA ? c.hc0 + wb : (rel == 0 ? c.stale_idx : rel);
+  TCHECK(5, hh < SMEM_TBL);
   const uint32_t t = c.tbl[hh];
   int I, Q;
   load_sample(c.tile, c.fmt, i, I, Q);
@@ -145,7 +153,7 @@ __device__ __forceinline__ void eval_sample(const SampleCtx &c, int i, int (&sum
 template <int NT, int H>
 __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx &sc, const uint32_t tile_addr, const uint32_t tbl_addr,
                                           const uint32_t alias_addr, const uint32_t vlut_lane, const PipeK K, const int nsamp,
-                                          const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB) {
+                                          const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB, const SegBounds bnd_in) {
   // Which run of segments a thread owns: consecutive runs start 43 bytes apart in the tile (H = 11), i.e. lanes l and
   // l+3 of a warp would read the same bank (4-way conflicts on the two window loads of every segment); stepping
   // through the runs with stride 7 spreads a warp over the banks (2-way).
@@ -183,9 +191,15 @@ __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx 
   } else
     hp = tbl_addr + 4u * (p.hc0 + m0);
   const uint32_t s = seg_start(m0, nk05, p.dinv);
+  SegBounds bnd = bnd_in;
+  if (clsB && m0 == w1) {  // alias table of this ring slot
+    bnd.bits_lo = alias_addr;
+    bnd.bits_hi = alias_addr + 4u * 48u;
+  }
+  TCHECK(4, nv == 0 || s + 7u * nv <= (uint32_t)nsamp);  // owned segments lie inside the block
   int pE, pP, pL;
   correlate_segments<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 7u * p.kinc, hp, (int)nv,
-                        vlut_lane, K, pE, pP, pL);
+                        vlut_lane, K, pE, pP, pL, bnd);
   {
     int v[6];
     unpack_lanes(pL, v[0], v[1]);

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
     while ((unsigned)(v = *slot) != ticket) __nanosleep(100);
     __threadfence();  // acquire: the state the previous slice of this channel stored
     s_item = (int)(v >> 32);
+    TCHECK(6, (unsigned)s_item < wq->total);  // the item behind the ticket exists
   }
   __syncthreads();
   const int item = queued ? s_item : (int)blockIdx.x;
@@ -208,6 +209,11 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
     cs.halted = (prev_flags >> 1) & 1;
     cs.dump_count = a.dump_count ? __ldcg(&a.dump_count[s * NCH + ch]) : (slice > 0 ? __ldcg(&wq->dumpcnt[chan_id]) : 0);
     first_block = rx->blocks_done + slice_first;
+#ifdef TRACK_CHECK
+    // hand-over: bit 2 marks a channel whose slice is running; the CTA that ran the previous slice cleared it with the
+    // store of its state, before it pushed this item
+    TCHECK(7, (atomicOr(&a.chan_flags[s * NCH + ch], 4) & 4) == 0);
+#endif
     sp.stale_bits = 0;
     if (nblocks > 0 && !rx->halted && !cs.halted) {
       prepare_block(cs, sp, a, tbl_prn);
@@ -454,9 +460,17 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
         bp.seg = p3.y;
         bp.dinv = params[slot].dinv;
         const SampleCtx sc{cph0, kph0, cinc, kinc, hc0, w1, stale_idx, tile, tbl, lut, fmt};
+        // what the segment loop may read: the tile plus the 48 bytes idle trailing segments run past it (the other tile or
+        // the mixer table follow), the code-table window, the mixer table
+        const SegBounds bnd{smem_u32(tile), smem_u32(tile) + (uint32_t)tile_bytes + 64u, smem_u32(tbl), smem_u32(tbl) + 4u * SMEM_TBL,
+#ifdef TRACK_CHECK_SELFTEST  // a deliberately wrong bound: the check must fire (tools/gpu_evidence.sh)
+                            smem_u32(vlut), smem_u32(vlut) + 64u * 32u * 4u};
+#else
+                            smem_u32(vlut), smem_u32(vlut) + 128u * 32u * 4u};
+#endif
         if (bp.seg)
           seg_block<CT, SEGH>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
-                              PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB);
+                              PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
         else
           generic_block<CT>(sc, a.nsamp, ctid, sumA, sumB, anyB);
       } else {

@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
     L.gnssb200_track_run_host.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, i64, vp, C.c_int, vp]
     L.gnssb200_set_track_slice.argtypes = [vp, i64]
     L.gnssb200_set_track_variant.argtypes = [vp, C.c_int, C.c_int]
+    L.gnssb200_track_check_failures.argtypes = [vp]
     L.gnssb200_acq_serial.argtypes = [vp, vp, C.c_int, i64, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     L.gnssb200_launch_count.argtypes = [vp]
     L.gnssb200_launch_count.restype = i64

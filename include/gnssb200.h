@@ -214,6 +214,11 @@ int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks);
  * occ: 0 automatic, else the resident-CTAs-per-SM variant (2..6) that would be chosen for that many channels per SM. */
 int gnssb200_set_track_variant(gnssb200_handle *h, int form, int occ);
 
+/* Libraries built with -DTRACK_CHECK verify on the device every shared-memory address the correlator warps form and the
+ * work-queue / ring hand-over invariants; this returns the number of violations since the last call (and the count per
+ * check in out[8] when it is not NULL), -1 when the library was built without the checks. */
+int gnssb200_track_check_failures(unsigned out[8]);
+
 /* Host-buffer pipeline of gnssb200_track_run_host: blocks per stream and staging chunk (0 = automatic, about 384
  * blocks, at least 32 MiB per chunk); results do not depend on it.  The dump records of a multi-chunk run are read
  * back window by window while later chunks are still running when h_dumps is pinned (or registered) host memory;

@@ -380,9 +380,11 @@ def test_acq_serial_cell_map_equals_oracle_search(oracle_lib, track_record):
 
 
 def test_config5_width_kernels_agree():
-    """BASELINE config 5 width (64 streams x 12 channels), 0.6 s: the warp-specialised kernel under the work queue
-    (slices of 128 and of 333 blocks) and the independent barrier-synchronised kernel (GNSSB200_TRACK_WS=0, its own
-    process) produce the same SHA-256 over all ~430 k dump records and all 64 final receiver states."""
+    """BASELINE config 5 width (64 streams x 12 channels), 0.6 s: the warp-specialised kernel in its half-chip-segment
+    form under the work queue (slices of 128 and of 333 blocks), in its fixed-sample-run form, and the independent
+    barrier-synchronised kernel (its own process each) produce the same SHA-256 over all ~430 k dump records and all 64
+    final receiver states -- four synchronisation schemes, one result (compute-sanitizer's racecheck is closed on this
+    pool; profiles/r02_sanitizer.txt holds the address / hand-over checks of the instrumented build)."""
     import os
     import subprocess
     import sys
@@ -390,17 +392,18 @@ def test_config5_width_kernels_agree():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     tool = os.path.join(root, "tools", "track_digest.py")
 
-    def run(slice_blocks, ws):
-        env = dict(os.environ, GNSSB200_TRACK_WS=str(ws))
+    def run(slice_blocks, form):
+        env = dict(os.environ, GNSSB200_TRACK_FORM=str(form))
         out = subprocess.run([sys.executable, tool, "64", "1172", str(slice_blocks)], env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
         line = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0].split()
         return line[1], int(line[2])
 
-    a = run(128, 1)
-    b = run(333, 1)
-    c = run(0, 0)
-    assert a == b == c and a[1] > 400000
+    a = run(128, 3)
+    b = run(333, 3)
+    c = run(128, 2)
+    d = run(0, 1)
+    assert a == b == c == d and a[1] > 400000
 
 
 def _run_host_pinned(eng, recs, nblk, cap, cnt_init=None):
