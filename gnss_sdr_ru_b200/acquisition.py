@@ -153,7 +153,7 @@ class AcquisitionEngine:
         nb = self.num_bins(settings)
         n_sv = len(settings.acqSatelliteList)
         dev = torch.device("cuda", torch.cuda.current_device())
-        rows = torch.zeros(n_sv * nb * abi.ACQ_ROW_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        rows = torch.zeros(n_sv * nb * np.dtype(abi.ACQ_ROW_DTYPE).itemsize, dtype=torch.uint8, device=dev)
         self.search_device(d_iq_ptr, n_samples, settings, rows.data_ptr(), fmt=fmt, part_index=rank, part_count=world,
                            stream=torch.cuda.current_stream().cuda_stream)
         gathered = torch.empty(world * rows.numel(), dtype=torch.uint8, device=dev)

@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
       mbar_arrive(&pfull[slot]);  // release: the stores above are visible to whoever observes the phase
     };
     bool event = block_is_event(sp, a, nblocks <= 1);
+#ifdef EXP_ALL_QUIET  // timing experiment only (results are wrong): every block handled as a quiet block
+    if (sp.mode == MODE_FAST && nblocks > 1) event = false;
+#endif
     publish(0, sp, event);
     uint32_t ev_phase = 0;
 #ifdef TRACK_PROFILE
@@ -291,6 +294,9 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
       if (!event) {  // quiet block: nothing leaves the correlator threads
         advance_quiet(sp, a);
         event = block_is_event(sp, a, b + 2 == nblocks);
+#ifdef EXP_ALL_QUIET
+        if (sp.mode == MODE_FAST && b + 2 != nblocks) event = false;
+#endif
         publish(nslot, sp, event);
 #ifdef TRACK_PROFILE
         n_q++;
@@ -310,6 +316,17 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
         if (!last) prepare_block_state(cs, sp, a);  // sp now describes block b+1 as far as the correlator state decides it
       }
       CP(c_fin)
+#ifdef EXP_EARLY_PUBLISH  // timing experiment only (results are wrong): what the kernel would do without the dump -> ISR -> next block dependency
+      bool early = false;
+      ChRegs saved_r = cs.r;
+      if (was_mode == MODE_FAST && !last) {
+        StepParams t = sp;
+        prepare_block_regs(cs, t, a, tbl_prn);
+        t.stale_bits = t.mode == MODE_FAST ? tbl[t.stale_idx] : 0u;
+        publish(nslot, t, block_is_event(t, a, b + 2 == nblocks));
+        early = true;
+      }
+#endif
       if (was_mode == MODE_FAST) {
         int A[6], B[6];
         mbar_wait(&tfull, ev_phase);
@@ -346,6 +363,13 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
           isr = true;
       }
       CP(c_words)
+#ifdef EXP_EARLY_PUBLISH
+      if (early) {
+        cs.r.w_carr_hi = saved_r.w_carr_hi; cs.r.w_carr_lo = saved_r.w_carr_lo; cs.r.w_code_hi = saved_r.w_code_hi;
+        cs.r.w_code_lo = saved_r.w_code_lo; cs.r.w_slew = saved_r.w_slew;
+        cs.halted = 0;
+      }
+#endif
       if (cs.halted || was_mode == MODE_IDLE)  // an idle channel has no ISR: nothing can change any more
         sp.mode = MODE_STOP;
       else if (!last) {
@@ -356,6 +380,9 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
       if (!last) {
         event = block_is_event(sp, a, b + 2 == nblocks);
         CP(c_cls)
+#ifdef EXP_EARLY_PUBLISH
+        if (!early)
+#endif
         publish(nslot, sp, event);
       }
       CP(c_params)
