@@ -293,6 +293,11 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
         env_seg = e ? atoi(e) : 1;
       }
       if (!env_seg && form == 0) seg = false;
+      // Up to one channel per SM the run is bound by each channel's own block-to-block latency, and there 256 threads
+      // with 32 consecutive samples each finish a block sooner than 96 threads with 11 segments each (measured, 2 s of
+      // signal: 1 stream 63 k vs 52 k, 8 streams 494 k vs 412 k channel*Msamples/s; from 16 streams on the segment
+      // form is ahead: 721 k vs 691 k, 64 streams 1865 k vs 1436 k).
+      if (form == 0 && per_sm <= 1) seg = false;
       if (form >= 3) seg = true;  // forced: out-of-range blocks take the per-sample form inside the kernel
     }
     const size_t dyn_seg = dyn + 2048;  // slack to start the mixer table on a 2048-byte boundary
@@ -300,13 +305,13 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
       track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
-    else if (seg && (form == 5 || (form == 0 && per_sm <= 1)))
+    else if (seg && form == 5)
       track_ws_kernel<2, GNSSB200_FMT_PACKED2, 384, 3><<<items, 416, dyn_seg, st>>>(a, tile_bytes);
     else if (seg && form == 4 && per_sm >= 6)
       track_ws_kernel<6, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
     else if (seg && form == 4 && per_sm >= 4)
       track_ws_kernel<5, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
-    else if (seg && (form == 4 || (form == 0 && per_sm <= 2)))
+    else if (seg && form == 4)
       track_ws_kernel<3, GNSSB200_FMT_PACKED2, 192, 6><<<items, 224, dyn_seg, st>>>(a, tile_bytes);
     else if (seg && per_sm >= 6)
       track_ws_kernel<6, GNSSB200_FMT_PACKED2, 96, 11><<<items, 128, dyn_seg, st>>>(a, tile_bytes);

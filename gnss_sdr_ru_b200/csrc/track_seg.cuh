@@ -58,50 +58,42 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
                                                    const uint32_t k7, const uint32_t hp, const int nvalid, const uint32_t vlut_lane,
                                                    const PipeK K, int &accE, int &accP, int &accL, const SegBounds bnd) {
   int aE = 0, aP = 0, aL = 0;
-  TCHECK(0, ks < kinc || nvalid == 0);                            // a run starts on a code-NCO wrap
+  TCHECK(0, ks < kinc || nvalid == 0);                                    // a run starts on a code-NCO wrap
   TCHECK(1, hp >= bnd.bits_lo && hp + 4u * (H + 1) <= bnd.bits_hi + 4u);  // code-table entries of the run (+ one read ahead)
-  // Rolled on purpose: the body is ~75 instructions; unrolled H times every warp streams through > 10 KB of code per
-  // block and the warps of an SM, each somewhere else in it, keep missing the instruction cache (ncu: a sixth of the
-  // stalled warp-cycles were `no_instructions`).
   // Software pipelined: the two sample words and the code-table entry of segment j+1 are fetched while segment j is
-  // evaluated (a warp's issue rate in this loop is bound by its own dependency chain -- window load, shift, address,
-  // table load, sum -- not by the other warps; the prefetch takes the first shared-memory round trip off that chain).
+  // evaluated.  Rolled on purpose (#pragma unroll 1): unrolled H times every warp streams through > 10 KB of code per
+  // block and the warps of an SM, each somewhere else in it, keep missing the instruction cache (ncu: a sixth of the
+  // stalled warp-cycles were `no_instructions`, 13 % slower).
+  // Pipe balance (ncu + SASS): ALU and FMA pipes both take one warp instruction per two cycles; the loop is written so
+  // that neither carries much more than half of the ~75 instructions of a segment: LO phase by shift (IMAD.HI is slow),
+  // table address and the "eighth sample" selections as multiply-adds by the 0/1 flag `e8`.
   uint32_t a0 = (q >> 3) & ~3u;
   TCHECK(2, a0 >= bnd.tile_lo && a0 + 8u <= bnd.tile_hi);
   uint32_t lo = lds_u32(a0), hi = lds_u32(a0 + 4);
   uint32_t t = lds_u32(hp);
-  constexpr int UNR = SEG_UNROLL;
-#pragma unroll UNR
-  for (int j = 0; j < H; j++) {
+  uint32_t hq = hp;                                      // running table address: the loop counter
+  const uint32_t hq_valid = hp + 4u * (uint32_t)nvalid;  // segments at or past it do not count
+  const uint32_t hq_end = hp + 4u * (uint32_t)H;
+#pragma unroll 1
+  do {
     // eight 4-bit sample codes from bit address q (two aligned words, funnel shift by q mod 32)
-#ifdef SEG_NO_PIPELINE
-    if (j > 0) {
-      const uint32_t aa = (q >> 3) & ~3u;
-      lo = lds_u32(aa);
-      hi = lds_u32(aa + 4);
-      t = lds_u32(hp + 4u * (uint32_t)j);
-    }
-#endif
     const uint32_t wd = __funnelshift_r(lo, hi, q);
-    // 7 or 8 samples: the segment ends with the sample whose code step wraps
+    // 7 or 8 samples: the segment ends with the sample whose code step wraps; e8 = 1 when there are eight
     uint32_t u, c;
     asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(u), "=r"(c) : "r"(ks), "r"(k7));
-    const bool eight = c == 0;
-    ks = eight ? u + kinc : u;
-    q += eight ? 32u : 28u;
-    // next segment's words and table entry (one segment past the run for the last j: still inside the windows)
+    const uint32_t e8 = K.k1 - c;
+    ks = e8 * kinc + u;
+    q = e8 * 4u + (q + 28u);
+    // next segment's words and table entry (one segment past the run in the last round: still inside the windows)
     const uint32_t a = (q >> 3) & ~3u;
     TCHECK(2, a >= bnd.tile_lo && a + 8u <= bnd.tile_hi);  // sample window inside the tile (+ read-ahead slack)
-#ifndef SEG_NO_PIPELINE
     lo = lds_u32(a);
     hi = lds_u32(a + 4);
-    const uint32_t t_next = lds_u32(hp + 4u * (uint32_t)(j + 1));
-#endif
+    const uint32_t t_next = lds_u32(hq + 4u);
     int v[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      // entry offset = (phase*16 + code) * 128 bytes + lane*4.  Code part on the ALU pipe (shift, and-or), LO
-      // phase (top three bits of the carrier NCO), its scaling and the NCO step as IMADs on the FMA pipe.
+      // entry offset = (phase*16 + code) * 128 bytes + lane*4
       uint32_t sh;
       if (k == 0)
         sh = wd << 7;
@@ -111,34 +103,21 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
         sh = wd >> (4 * k - 7);
       uint32_t ca;
       asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(ca) : "r"(sh), "r"(vlut_lane));  // (sh & 0x780) | vlut_lane
-      // LO phase = top three bits of the carrier NCO: by multiplication (FMA pipe) or by shift (ALU pipe), alternating,
-      // so that the two half-rate pipes carry about the same number of instructions per segment
-#ifndef SEG_PHASE_SHF_MASK
-#define SEG_PHASE_SHF_MASK 0xFF
-#endif
-      const uint32_t idx = ((SEG_PHASE_SHF_MASK >> k) & 1) ? (cph >> 29) : __umulhi(cph, K.k8);
-      #ifndef SEG_ADDR_LEA_MASK
-#define SEG_ADDR_LEA_MASK 0x00
-#endif
-#ifndef SEG_STEP_ADD_MASK
-#define SEG_STEP_ADD_MASK 0xFF
-#endif
-      const uint32_t eaddr = ((SEG_ADDR_LEA_MASK >> k) & 1) ? (idx << 11) + ca : idx * K.k2048 + ca;
+      const uint32_t eaddr = (cph >> 29) * K.k2048 + ca;  // LO phase = top three bits of the carrier NCO
       TCHECK(3, eaddr >= bnd.vlut_lo && eaddr + 4u <= bnd.vlut_hi);  // mixer table entry
       v[k] = (int)lds_u32(eaddr);
-      if (k < 7) cph = ((SEG_STEP_ADD_MASK >> k) & 1) ? cph + cinc : cinc * K.k1 + cph;
+      if (k < 7) cph += cinc;
     }
-    if (eight) cph += cinc;
-    const int S = ((v[0] + v[1] + v[2]) + (v[3] + v[4] + v[5])) + (v[6] + (eight ? v[7] : 0));
-    if (j < nvalid) {
+    cph = e8 * cinc + cph;
+    const int S = (int)e8 * v[7] + (((v[0] + v[1] + v[2]) + (v[3] + v[4] + v[5])) + v[6]);
+    if (hq < hq_valid) {
       aE += sext8(t, 0) * S;
       aP += sext8(t, 1) * S;
       aL += sext8(t, 2) * S;
     }
-#ifndef SEG_NO_PIPELINE
     t = t_next;
-#endif
-  }
+    hq += 4u;
+  } while (hq != hq_end);
   accE = aE;
   accP = aP;
   accL = aL;
