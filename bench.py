@@ -330,6 +330,22 @@ def run_ours(args):
     e2e_value = total_chan_samples * args.steps / float(te.item()) / 1e6
     h2d = S * stream_bytes + S * C.sizeof(abi.Rx)
     d2h = S * 12 * cap * 48 + S * 12 * 4
+    # the ceiling of that figure on this box: every rank copying the same pinned records at the same time and nothing
+    # else (what the host's memory system and the PCIe links deliver to N GPUs at once)
+    barrier()
+    for _ in range(2):
+        d_if.copy_(h_if, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d_if.copy_(h_if, non_blocking=True)
+    torch.cuda.synchronize()
+    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    barrier()
+    h2d_gbs = 3 * S * stream_bytes / float(tc.item()) / 1e9  # per GPU, at the pace of the slowest rank
+    e2e_ceiling = total_chan_samples / (S * stream_bytes / (h2d_gbs * 1e9)) / 1e6
 
     # ---- roofline of the tracking kernel ----
     peak, peak_src = load_peaks()
@@ -520,7 +536,8 @@ def run_ours(args):
                    "streams_per_gpu": S, "blocks_per_stream": nblk,
                    "channels_tracking_at_end": sum(1 for x in states if x == 4), "channels": len(states),
                    "c5_strong": strong},
-        "e2e": {"value": e2e_value, "unit": "channel*Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": "channel*Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "h2d_GBs_per_gpu_all_ranks_copying": h2d_gbs, "copy_bound_ceiling": e2e_ceiling, "frac_of_ceiling": e2e_value / e2e_ceiling},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu, "parity_vs_reference": parity,
         "acq": acq, "tracking_other_shapes": also,
     }

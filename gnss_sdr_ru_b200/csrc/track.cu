@@ -236,6 +236,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<1, GNSSB200_FMT_PACKED2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<4, GNSSB200_FMT_PACKED2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<6, GNSSB200_FMT_PACKED2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_PACKED2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
@@ -328,6 +329,8 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       track_ws_kernel<4, GNSSB200_FMT_PACKED2, 128><<<items, 160, dyn, st>>>(a, tile_bytes);
     else if (per_sm >= 3)
       track_ws_kernel<3, GNSSB200_FMT_PACKED2, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
+    else if (occ == 1 && nsamp % 16 == 0)  // 512 threads x 16 samples (experiments: shorter blocks for lone channels)
+      track_ws_kernel<1, GNSSB200_FMT_PACKED2, 512><<<items, 544, dyn, st>>>(a, tile_bytes);
     else
       track_ws_kernel<2, GNSSB200_FMT_PACKED2, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
   } else
