@@ -8,6 +8,7 @@ N_CHANNELS = 12
 FMT_INT8_IQ = 0
 FMT_PACKED2 = 1
 FMT_INT8_I = 2
+PRN_GLONASS = 1 << 10  # PRN register value that selects the GLONASS ST code (gnssb200.h)
 
 SYS_GPS = 0
 SYS_GLONASS = 1
@@ -41,6 +42,11 @@ class Cfg(C.Structure):
         ("pll_i3", C.c_int32),
         ("dll_i1", C.c_int32),
         ("dll_i2", C.c_int32),
+        ("pad_", C.c_int32),
+        ("glonass_carrier_if", C.c_double),
+        ("glonass_code_f", C.c_double),
+        ("glonass_carrier_ref", C.c_int64),
+        ("glonass_code_ref", C.c_int64),
     ]
 
 
@@ -85,7 +91,7 @@ class Chan(C.Structure):
         ("bit", C.c_int32),
         ("search_max_PRN_delay", C.c_int32),
         ("search_max_f", C.c_int32),
-        ("pad_", C.c_int32),
+        ("system", C.c_int32),
     ]
 
 

@@ -41,6 +41,8 @@ extern "C" void gnssb200_cfg_default(gnssb200_cfg *c) {
   c->Bnd = 2;
   c->pll_integ_ms = 1;
   c->dll_integ_ms = 1;
+  c->glonass_carrier_if = 0.0;
+  c->glonass_code_f = 511000.0;
 }
 
 extern "C" void gnssb200_cfg_derive(gnssb200_cfg *c) {
@@ -48,6 +50,8 @@ extern "C" void gnssb200_cfg_derive(gnssb200_cfg *c) {
   const double code_res = c->clock_mult * c->samp_rate / pow(2.0, (double)c->code_nco_bits);
   c->gps_code_ref = (int64_t)(c->gps_code_f / code_res);
   c->gps_carrier_ref = (int64_t)(c->gps_carrier_if / carr_res);
+  c->glonass_code_ref = (int64_t)(c->glonass_code_f / code_res);        // correlator.c:117
+  c->glonass_carrier_ref = (int64_t)(c->glonass_carrier_if / carr_res);  // correlator.c:118
   c->d_freq = (int64_t)((double)(int)c->freq_bin_width / carr_res);
   c->tic_ref = (int64_t)(c->samp_rate * c->tic_period);
   const double a2 = 1.414;
@@ -101,8 +105,17 @@ extern "C" void gnssb200_rx_cold_allocate(gnssb200_rx *rx, const gnssb200_cfg *c
     k->search_max_f = 5;
     k->ms_set = 0;
   }
-  for (int ch = 0; ch < NCH; ch++)
-    if (prn[ch] > 0) gnssb200_ch_cntl(rx, ch, prn[ch]);
+  for (int ch = 0; ch < NCH; ch++) {
+    if (prn[ch] <= 0) continue;
+    gnssb200_ch_cntl(rx, ch, prn[ch]);
+    if (prn[ch] == GNSSB200_PRN_GLONASS) {  // the hooks of the reference put to use (gnssb200.h)
+      gnssb200_chan *k = &rx->chan[ch];
+      k->system = 1;
+      k->search_max_PRN_delay = 1021;  // osgnss_next_step.c:54
+      gnssb200_ch_carrier(rx, c, ch, c->glonass_carrier_ref);
+      gnssb200_ch_code(rx, c, ch, c->glonass_code_ref);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

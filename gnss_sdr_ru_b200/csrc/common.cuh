@@ -8,8 +8,20 @@
 
 #define NCH GNSSB200_N_CHANNELS
 #define HALF_CHIPS 2046
-#define TABLE_ROWS 34                       // rows 0 and 33 are zero
+#define TABLE_ROWS 37                       // rows 0, 33, 34 and 36 are zero; row 35 = GLONASS ST code
 #define TABLE_ENTRIES (TABLE_ROWS * HALF_CHIPS)
+#define GLO_ROW 35                          // E/P/L of the 511-chip ST code: 1022 entries, the rest of the row is zero
+#define GLO_HALF_CHIPS 1022
+
+// PRN register -> first entry of the channel's row in the flat E/P/L table (-1: no code, all reads give 0) and the
+// number of half chips after which the channel dumps.  GPS rows are addressed by the register value itself like in
+// correlator.c:193-198 (0..33; 0 and 33 are zero rows); GNSSB200_PRN_GLONASS selects the ST-code row.
+__host__ __device__ __forceinline__ long long code_table_base(int prn_reg) {
+  if (prn_reg == GNSSB200_PRN_GLONASS) return (long long)GLO_ROW * HALF_CHIPS;
+  return (prn_reg >= 0 && prn_reg <= 33) ? (long long)prn_reg * HALF_CHIPS : -1;
+}
+__host__ __device__ __forceinline__ int code_period(int prn_reg) { return prn_reg == GNSSB200_PRN_GLONASS ? GLO_HALF_CHIPS : HALF_CHIPS; }
+__host__ __device__ __forceinline__ bool code_has_fast_row(int prn_reg) { return (prn_reg >= 1 && prn_reg <= 32) || prn_reg == GNSSB200_PRN_GLONASS; }
 
 // library-wide error slot (api.cu)
 void gnssb200_set_error(int code, const char *what, const char *file, int line);

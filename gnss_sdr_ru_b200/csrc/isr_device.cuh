@@ -220,6 +220,10 @@ __device__ __forceinline__ int dev_atan2_i32(int y, int x) {
 #define A_IE 4
 #define A_QE 5
 
+// reference words of the channel's system: the GPS ones of osgpsisr.c, or the GLONASS hooks of correlator.c:116-118
+__device__ __forceinline__ long long dev_carrier_ref(const gnssb200_chan &k, const DevCfg &c) { return k.system ? c.glonass_carrier_ref : c.gps_carrier_ref; }
+__device__ __forceinline__ long long dev_code_ref(const gnssb200_chan &k, const DevCfg &c) { return k.system ? c.glonass_code_ref : c.gps_code_ref; }
+
 __device__ __forceinline__ void dev_isr_search(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   if (abs(k.n_freq) <= k.search_max_f) {
     long long pm = dev_mag(k.accum[A_IP], k.accum[A_QP]);
@@ -235,14 +239,14 @@ __device__ __forceinline__ void dev_isr_search(gnssb200_chan &k, ChRegs &r, cons
     if (k.codes == k.search_max_PRN_delay) {
       k.n_freq += k.del_freq;
       k.del_freq = -(k.del_freq + dev_sgn(k.del_freq));
-      k.carrier_freq = c.gps_carrier_ref + k.carrier_cold_corr + c.d_freq * k.n_freq;
+      k.carrier_freq = dev_carrier_ref(k, c) + k.carrier_cold_corr + c.d_freq * k.n_freq;
       dev_ch_carrier(r, c, k.carrier_freq);
       k.codes = 0;
     }
   } else {
     k.n_freq = 0;
     k.del_freq = 1;
-    k.carrier_freq = c.gps_carrier_ref + k.carrier_cold_corr + c.d_freq * k.n_freq;
+    k.carrier_freq = dev_carrier_ref(k, c) + k.carrier_cold_corr + c.d_freq * k.n_freq;
     dev_ch_carrier(r, c, k.carrier_freq);
     k.codes = 0;
   }
@@ -264,7 +268,7 @@ __device__ __forceinline__ void dev_isr_confirm(gnssb200_chan &k, ChRegs &r, con
       k.ch_time = 0;
       k.ms_set = 0;
       k.oldCarrNco = k.oldCodeNco = k.oldCarrError = k.oldCodeError = 0;
-      k.codeFreqBasis = c.gps_code_ref;
+      k.codeFreqBasis = dev_code_ref(k, c);
       k.carrFreqBasis = k.carrier_freq;
       k.sign_pos = k.prev_sign_pos = 0;
     } else
@@ -389,8 +393,8 @@ __device__ __forceinline__ void dev_isr_loops(gnssb200_chan &k, ChRegs &r, const
 __device__ __forceinline__ void dev_isr_pull_in_words(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
   dev_isr_loops(k, r, c);
   if (k.ch_time + 1 == 3000) {  // the time-out below will reload the reference words
-    dev_ch_carrier(r, c, c.gps_carrier_ref);
-    dev_ch_code(r, c, c.gps_code_ref);
+    dev_ch_carrier(r, c, dev_carrier_ref(k, c));
+    dev_ch_code(r, c, dev_code_ref(k, c));
   }
 }
 __device__ __forceinline__ void dev_isr_pull_in_rest(gnssb200_chan &k, ChRegs &r, const DevCfg &c) {
@@ -421,8 +425,8 @@ __device__ __forceinline__ void dev_isr_pull_in_rest(gnssb200_chan &k, ChRegs &r
   if (k.ch_time == 3000) {
     k.del_freq = 1;
     k.n_freq = 0;
-    dev_ch_carrier(r, c, c.gps_carrier_ref);  // same words as dev_isr_pull_in_words wrote
-    dev_ch_code(r, c, c.gps_code_ref);
+    dev_ch_carrier(r, c, dev_carrier_ref(k, c));  // same words as dev_isr_pull_in_words wrote
+    dev_ch_code(r, c, dev_code_ref(k, c));
     k.codes = 0;
     k.ch_time = 0;
     k.state = 1;

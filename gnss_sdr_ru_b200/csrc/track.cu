@@ -142,6 +142,22 @@ void build_code_table_host(uint32_t *table) {
       table[prn * HALF_CHIPS + h] = (uint32_t)(e & 0xff) | ((uint32_t)(p & 0xff) << 8) | ((uint32_t)(l & 0xff) << 16);
     }
   }
+  {  // GLONASS ST code as NAM/rtl/code_gen.v:121-133 generates it: nine-stage register, all ones after the PRN-key
+     // write, output stage g3[2], feedback g3[4]^g3[0] (= SCI/GLONASS/L1/include/generateSTcode.sci:35-42); replicas at
+     // half-chip spacing like the C/A rows with the period 1022
+    int chip[511];
+    unsigned g3 = 0x1FF;
+    for (int c = 0; c < 511; c++) {
+      chip[c] = (g3 >> 2) & 1;
+      g3 = (g3 >> 1) | ((((g3 >> 4) ^ g3) & 1u) << 8);
+    }
+    for (int h = 0; h < GLO_HALF_CHIPS; h++) {
+      const int e = 2 * chip[(h % GLO_HALF_CHIPS) >> 1] - 1;
+      const int p = 2 * chip[((h + 1) % GLO_HALF_CHIPS) >> 1] - 1;
+      const int l = 2 * chip[((h + 2) % GLO_HALF_CHIPS) >> 1] - 1;
+      table[GLO_ROW * HALF_CHIPS + h] = (uint32_t)(e & 0xff) | ((uint32_t)(p & 0xff) << 8) | ((uint32_t)(l & 0xff) << 16);
+    }
+  }
 }
 
 size_t track_sched_bytes(int n_streams) {  // work-queue storage for a handle with n_streams receivers

@@ -382,13 +382,13 @@ __device__ __forceinline__ void prepare_block_regs(ChanShared &cs, StepParams &s
   }
   sp.cinc = (uint32_t)((r.w_carr_hi << 16) + r.w_carr_lo);
   sp.kinc = (uint32_t)((r.w_code_hi << 16) + r.w_code_lo) << 1;
-  const long long slew_dump = (long long)r.w_slew + HALF_CHIPS;  // :172
+  const long long slew_dump = (long long)r.w_slew + code_period(r.w_prn);  // :172 (1022 for a GLONASS channel)
   sp.slew_dump = (uint32_t)slew_dump;
   const long long w1 = ((long long)sp.hc0 + 1 >= slew_dump) ? 1 : slew_dump - sp.hc0;
   const unsigned long long wtot = ((unsigned long long)sp.kph0 + (unsigned long long)n * sp.kinc) >> 32;
   sp.w1 = (uint32_t)w1;
   sp.stale_idx = (uint32_t)(sp.hc0 + w1);
-  bool fast = (r.w_prn == tbl_prn) && r.w_prn >= 1 && r.w_prn <= 32 && slew_dump >= 1 && slew_dump < 65536 &&
+  bool fast = (r.w_prn == tbl_prn) && code_has_fast_row(r.w_prn) && slew_dump >= 1 && slew_dump < 65536 &&
               (long long)wtot < w1 + slew_dump && (wtot + 40) < SMEM_TBL && (sp.hc0 + w1 + 40) < SMEM_TBL &&
               n < (1ll << 30) && sp.kinc >= 1u && sp.kinc < (1u << 30);
   sp.mode = fast ? MODE_FAST : MODE_SERIAL;
@@ -477,12 +477,12 @@ __device__ __noinline__ void serial_block(ChanShared &cs, const StepParams &sp, 
                                           const uint8_t *blk) {
   gnssb200_corr &g = cs.g;
   ChRegs &r = cs.r;
-  const long long row = (long long)r.w_prn * HALF_CHIPS;
-  const int dump_at = r.w_slew + HALF_CHIPS;
+  const long long row = code_table_base(r.w_prn);
+  const int dump_at = r.w_slew + code_period(r.w_prn);
   uint16_t hc = (uint16_t)g.half_chip;
   auto bits_at = [&](uint16_t hh) -> uint32_t {
     long long f = row + hh;
-    return (f >= 0 && f < TABLE_ENTRIES) ? code_table[f] : 0u;
+    return (row >= 0 && f < TABLE_ENTRIES) ? code_table[f] : 0u;
   };
   uint32_t t = bits_at(hc);
   int cE = sext8(t, 0), cP = sext8(t, 1), cL = sext8(t, 2);

@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
   fill_lo_lut(lut);
   if (tid < 12) totals[tid] = 0;
   for (int i = tid; i < SMEM_TBL; i += blockDim.x) {
-    long long f = (long long)tbl_prn * HALF_CHIPS + i;
-    tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+    long long f = code_table_base(tbl_prn) + i;
+    tbl[i] = (code_has_fast_row(tbl_prn) && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   if (packed_native) {
     for (int i = tid; i < 128 * 32; i += blockDim.x) {
@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
     }
   }
   if (tid < 48) {
-    long long f = (long long)tbl_prn * HALF_CHIPS + tid;
-    alias_tbl[tid] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+    long long f = code_table_base(tbl_prn) + tid;
+    alias_tbl[tid] = (code_has_fast_row(tbl_prn) && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   for (int i = tid; i < 256; i += blockDim.x) {
     uint32_t wv = 0;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(MAXT, MINB) track_loop_kernel(const TrackArgs 
       sp_s.mode = MODE_STOP;
     sp_s.stale_bits = 0;
     if (sp_s.mode == MODE_FAST) {
-      const long long f = (long long)tbl_prn * HALF_CHIPS + sp_s.stale_idx;
+      const long long f = code_table_base(tbl_prn) + sp_s.stale_idx;
       sp_s.stale_bits = f < TABLE_ENTRIES ? a.code_table[f] : 0u;
     }
     alias_tbl[0] = sp_s.stale_bits;

@@ -178,13 +178,13 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
 
   if (tid < 12) totals[tid] = 0;
   for (int i = tid; i < SMEM_TBL; i += WS_THREADS) {
-    long long f = (long long)tbl_prn * HALF_CHIPS + i;
-    tbl[i] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+    long long f = code_table_base(tbl_prn) + i;
+    tbl[i] = (code_has_fast_row(tbl_prn) && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   if (tid < 96) {
     const int t = tid % 48;
-    long long f = (long long)tbl_prn * HALF_CHIPS + t;
-    alias_tbl[tid / 48][t] = (tbl_prn >= 1 && tbl_prn <= 32 && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
+    long long f = code_table_base(tbl_prn) + t;
+    alias_tbl[tid / 48][t] = (code_has_fast_row(tbl_prn) && f < TABLE_ENTRIES) ? a.code_table[f] : 0u;
   }
   __syncthreads();  // tbl complete before the control lane looks up stale bits
   const int b8 = ch << 3;

@@ -123,9 +123,19 @@ class TrackingEngine:
         k.n_freq = n_freq
         # del_freq sequence 1,-2,3,-4..: after reaching n the next step is -(2n) for n>0, 1-2n for n<=0
         k.del_freq = -2 * n_freq if n_freq > 0 else 1 - 2 * n_freq
-        k.carrier_freq = self.cfg.gps_carrier_ref + k.carrier_cold_corr + self.cfg.d_freq * n_freq
+        ref = self.cfg.glonass_carrier_ref if k.system else self.cfg.gps_carrier_ref
+        k.carrier_freq = ref + k.carrier_cold_corr + self.cfg.d_freq * n_freq
         k.codes = 0
         self.ch_carrier(s, ch, k.carrier_freq)
+
+    def set_glonass_channel(self, s: int, ch: int, fch: int):
+        """Frequency channel of a GLONASS correlator channel (allocated with PRN register abi.PRN_GLONASS): the FDMA
+        offset fch * 562.5 kHz in carrier-NCO units goes into carrier_cold_corr -- the correction the channel logic adds
+        to the reference word (osgpsisr.c:446,454); the firmware's GLNS_L1_CARR_REF_STEP = 7549747 at 16 MHz x 5."""
+        k = self.rx[s].chan[ch]
+        res = self.cfg.clock_mult * self.cfg.samp_rate / 2.0 ** self.cfg.carrier_nco_bits
+        k.carrier_cold_corr = int(fch * int(562500.0 / res))
+        self.ch_carrier(s, ch, self.cfg.glonass_carrier_ref + k.carrier_cold_corr)
 
     def upload(self):
         check(self.L.gnssb200_upload_rx(self.h, 0, self.n_streams, C.addressof(self.rx)), "gnssb200_upload_rx")

@@ -73,7 +73,23 @@ typedef struct gnssb200_cfg {
   int64_t gps_carrier_ref, gps_code_ref, d_freq;   /* correlator.c:114-121 */
   int64_t tic_ref;                                 /* correlator.c:124 */
   int32_t pll_i1, pll_i2, pll_i3, dll_i1, dll_i2;  /* osgpsisr.c:252-342 */
+  int32_t pad_;
+  /* GLONASS channels of the integer correlator (see GNSSB200_PRN_GLONASS below) */
+  double glonass_carrier_if; /* GLONASS_CARRIER_IF 0.0e6            globals.h:19 */
+  double glonass_code_f;     /* GLONASS_CODE_F 511000               globals.h:20 */
+  int64_t glonass_carrier_ref, glonass_code_ref; /* derived, correlator.c:116-118 */
 } gnssb200_cfg;
+
+/* GLONASS in the integer correlator.  The C reference carries only the hooks (glonass_code_ref /
+ * glonass_carrier_ref, correlator.c:116-118; chan[].system "for future use", structs.h:88; "1021 for GLONASS",
+ * osgnss_next_step.c:54); the behaviour is the one of the correlator the C code emulates, NAM/rtl/code_gen.v:
+ * writing bit 10 of the PRN register selects the 511-chip ST code (g3 register, :121-139) and a code period of
+ * 1022 half chips (:236-272) -- the firmware's `outpw(PRN_KEY, 1<<10)`.  Here: a channel whose PRN register holds
+ * GNSSB200_PRN_GLONASS correlates against the ST-code row of the E/P/L table (built like the C/A rows,
+ * correlator.c:84-89, with 1022 for 2046; entries past the row are 0) and dumps every 1022 + slew half chips;
+ * a channel with chan.system = 1 takes glonass_code_ref / glonass_carrier_ref where the channel logic of
+ * osgpsisr.c uses the GPS ones, its frequency-channel offset k*562.5 kHz goes into carrier_cold_corr. */
+#define GNSSB200_PRN_GLONASS (1 << 10)
 
 void gnssb200_cfg_default(gnssb200_cfg *cfg); /* reference defaults (globals.h) */
 void gnssb200_cfg_derive(gnssb200_cfg *cfg);  /* correlator_init + init_tracking_loops_parameter */
@@ -99,7 +115,7 @@ typedef struct gnssb200_chan {
   uint64_t ms_sign;
   int32_t bit;
   int32_t search_max_PRN_delay, search_max_f;
-  int32_t pad_;
+  int32_t system;           /* channel_gnss_system_enum: 0 GPS, 1 GLONASS (structs.h:78-88) */
 } gnssb200_chan;
 
 /* Per-channel correlator state: struct gp2021_channel + ms/bit counters

@@ -27,7 +27,9 @@
 
 #define NCH GNSSB200_N_CHANNELS
 #define HALF_CHIPS 2046
-#define TABLE_ROWS 34
+#define TABLE_ROWS 37 /* rows 0, 33, 34, 36 zero; row 35: GLONASS ST code (1022 entries, then zeros) */
+#define GLO_ROW 35
+#define GLO_HALF_CHIPS 1022
 
 static int8_t tab_early[TABLE_ROWS * HALF_CHIPS];
 static int8_t tab_prompt[TABLE_ROWS * HALF_CHIPS];
@@ -60,7 +62,42 @@ static void build_tables(void) {
       tab_late[prn * HALF_CHIPS + h] = (int8_t)(2 * chip[((h + 2) % HALF_CHIPS) >> 1] - 1);
     }
   }
+  { /* GLONASS ST code: the g3 register of NAM/rtl/code_gen.v:121-133 (all ones after the PRN-key write, output
+       g3[2], feedback g3[4]^g3[0], shifting towards bit 0); replicas like the C/A rows with the period 1022.
+       An extension: the C reference has only the hooks for it (include/gnssb200.h, GNSSB200_PRN_GLONASS). */
+    int8_t chip[511];
+    unsigned g3 = 0x1FF;
+    for (int k = 0; k < 511; k++) {
+      chip[k] = (int8_t)((g3 >> 2) & 1);
+      unsigned fb = ((g3 >> 4) ^ g3) & 1u;
+      g3 = (g3 >> 1) | (fb << 8);
+    }
+    for (int h = 0; h < GLO_HALF_CHIPS; h++) {
+      tab_early[GLO_ROW * HALF_CHIPS + h] = (int8_t)(2 * chip[((h + 0) % GLO_HALF_CHIPS) >> 1] - 1);
+      tab_prompt[GLO_ROW * HALF_CHIPS + h] = (int8_t)(2 * chip[((h + 1) % GLO_HALF_CHIPS) >> 1] - 1);
+      tab_late[GLO_ROW * HALF_CHIPS + h] = (int8_t)(2 * chip[((h + 2) % GLO_HALF_CHIPS) >> 1] - 1);
+    }
+  }
   tables_ready = 1;
+}
+
+/* PRN register -> first entry of the channel's row (-1: no code) and its dump period in half chips */
+static long code_table_base(int prn_reg) {
+  if (prn_reg == GNSSB200_PRN_GLONASS) return (long)GLO_ROW * HALF_CHIPS;
+  return (prn_reg >= 0 && prn_reg <= 33) ? (long)prn_reg * HALF_CHIPS : -1;
+}
+static int code_period(int prn_reg) { return prn_reg == GNSSB200_PRN_GLONASS ? GLO_HALF_CHIPS : HALF_CHIPS; }
+static long long carrier_ref_of(const gnssb200_chan *k, const gnssb200_cfg *c) { return k->system ? c->glonass_carrier_ref : c->gps_carrier_ref; }
+static long long code_ref_of(const gnssb200_chan *k, const gnssb200_cfg *c) { return k->system ? c->glonass_code_ref : c->gps_code_ref; }
+
+/* E/P/L entry (which = 0 early, 1 prompt, 2 late) of half chip h for a PRN register value: for tests of the tables */
+int orc_code_bit(int which, int prn_reg, int h) {
+  build_tables();
+  const long base = code_table_base(prn_reg);
+  if (base < 0) return 0;
+  const int8_t *t = which == 0 ? tab_early : (which == 1 ? tab_prompt : tab_late);
+  const long f = base + h;
+  return (f >= 0 && f < (long)TABLE_ROWS * HALF_CHIPS) ? t[f] : 0;
 }
 
 /* flat table read with the reference's row spill-over; outside the 34 rows -> 0 */
@@ -104,6 +141,8 @@ void orc_cfg_default(gnssb200_cfg *c) {
   c->Bnd = 2;
   c->pll_integ_ms = 1;
   c->dll_integ_ms = 1;
+  c->glonass_carrier_if = 0.0;   /* globals.h:19 */
+  c->glonass_code_f = 511000.0;  /* globals.h:20 */
 }
 
 void orc_cfg_derive(gnssb200_cfg *c) {
@@ -111,6 +150,8 @@ void orc_cfg_derive(gnssb200_cfg *c) {
   double code_delta = c->clock_mult * c->samp_rate / pow(2.0, c->code_nco_bits);
   c->gps_code_ref = (int64_t)(c->gps_code_f / code_delta);
   c->gps_carrier_ref = (int64_t)(c->gps_carrier_if / carr_delta);
+  c->glonass_code_ref = (int64_t)(c->glonass_code_f / code_delta);       /* correlator.c:117 */
+  c->glonass_carrier_ref = (int64_t)(c->glonass_carrier_if / carr_delta); /* correlator.c:118 */
   c->d_freq = (int64_t)((int)c->freq_bin_width / carr_delta); /* (int) binds to freq_bin_width, :121 */
   c->tic_ref = (int64_t)(c->samp_rate * c->tic_period);
   /* loop filters, Kaplan & Hegarty pp.179-183 as coded at osgpsisr.c:252-342 */
@@ -179,8 +220,17 @@ void orc_rx_cold_allocate(gnssb200_rx *rx, const gnssb200_cfg *c, const int32_t 
     k->search_max_f = 5;
     k->ms_set = 0;
   }
-  for (int ch = 0; ch < NCH; ch++)
-    if (prn[ch] > 0) orc_ch_cntl(rx, ch, prn[ch]);
+  for (int ch = 0; ch < NCH; ch++) {
+    if (prn[ch] <= 0) continue;
+    orc_ch_cntl(rx, ch, prn[ch]);
+    if (prn[ch] == GNSSB200_PRN_GLONASS) { /* the reference's hooks put to use: system flag, 1021 delays, GLONASS words */
+      gnssb200_chan *k = &rx->chan[ch];
+      k->system = 1;
+      k->search_max_PRN_delay = 1021; /* osgnss_next_step.c:54 */
+      orc_ch_carrier(rx, c, ch, c->glonass_carrier_ref);
+      orc_ch_code(rx, c, ch, c->glonass_code_ref);
+    }
+  }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -202,7 +252,7 @@ void orc_sim_gp2021(gnssb200_rx *rx, const gnssb200_cfg *c, const int8_t *IF, lo
     const int base = ch << 3;
     int *W = rx->reg_write, *R = rx->reg_read;
     gnssb200_corr *g = &rx->corr[ch];
-    const int dump_at = W[base + 0x84] + HALF_CHIPS; /* :172, read once per block */
+    const int dump_at = W[base + 0x84] + code_period(W[base]); /* :172, read once per block (1022 for a GLONASS channel) */
 
     if (W[base + 7] != -1) { /* :177-182 epoch load */
       R[base + 7] = W[base + 7];
@@ -214,7 +264,7 @@ void orc_sim_gp2021(gnssb200_rx *rx, const gnssb200_cfg *c, const int8_t *IF, lo
 
     const uint32_t cinc = (uint32_t)((W[base + 3] << 16) + W[base + 4]); /* :187 */
     const uint32_t kinc = (uint32_t)((W[base + 5] << 16) + W[base + 6]) << 1; /* :189,:245 */
-    const long row = (long)W[base] * HALF_CHIPS;
+    const long row = code_table_base(W[base]) >= 0 ? code_table_base(W[base]) : (long)TABLE_ROWS * HALF_CHIPS; /* no code: reads give 0 */
     uint16_t hc = (uint16_t)g->half_chip;
     int bp = tab_at(tab_prompt, row + hc), bl = tab_at(tab_late, row + hc), be = tab_at(tab_early, row + hc); /* :196-198 */
     const int8_t *p = IF;
@@ -367,14 +417,14 @@ static void isr_search(gnssb200_rx *rx, const gnssb200_cfg *c, int ch) {
     if (k->codes == k->search_max_PRN_delay) {
       k->n_freq += k->del_freq;
       k->del_freq = -(k->del_freq + sgn(k->del_freq));
-      k->carrier_freq = c->gps_carrier_ref + k->carrier_cold_corr + c->d_freq * k->n_freq;
+      k->carrier_freq = carrier_ref_of(k, c) + k->carrier_cold_corr + c->d_freq * k->n_freq;
       orc_ch_carrier(rx, c, ch, k->carrier_freq);
       k->codes = 0;
     }
   } else {
     k->n_freq = 0;
     k->del_freq = 1;
-    k->carrier_freq = c->gps_carrier_ref + k->carrier_cold_corr + c->d_freq * k->n_freq;
+    k->carrier_freq = carrier_ref_of(k, c) + k->carrier_cold_corr + c->d_freq * k->n_freq;
     orc_ch_carrier(rx, c, ch, k->carrier_freq);
     k->codes = 0;
   }
@@ -398,7 +448,7 @@ static void isr_confirm(gnssb200_rx *rx, const gnssb200_cfg *c, int ch) {
       k->ch_time = 0;
       k->ms_set = 0;
       k->oldCarrNco = k->oldCodeNco = k->oldCarrError = k->oldCodeError = 0;
-      k->codeFreqBasis = c->gps_code_ref;
+      k->codeFreqBasis = code_ref_of(k, c);
       k->carrFreqBasis = k->carrier_freq;
       k->sign_pos = k->prev_sign_pos = 0;
     } else
@@ -476,8 +526,8 @@ static void isr_pull_in(gnssb200_rx *rx, const gnssb200_cfg *c, int ch) {
   if (k->ch_time == 3000) {                            /* :656-671 */
     k->del_freq = 1;
     k->n_freq = 0;
-    orc_ch_carrier(rx, c, ch, c->gps_carrier_ref);
-    orc_ch_code(rx, c, ch, c->gps_code_ref);
+    orc_ch_carrier(rx, c, ch, carrier_ref_of(k, c));
+    orc_ch_code(rx, c, ch, code_ref_of(k, c));
     k->codes = 0;
     k->ch_time = 0;
     k->state = 1;

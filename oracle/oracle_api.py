@@ -68,6 +68,7 @@ class Oracle:
             L.orc_ch_code.argtypes = [C.POINTER(abi.Rx), C.POINTER(abi.Cfg), C.c_int, C.c_int64]
             L.orc_code_bits.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int * 3)]
             L.orc_lo_table.argtypes = [C.c_int, C.POINTER(C.c_int * 2)]
+            L.orc_code_bit.argtypes = [C.c_int, C.c_int, C.c_int]
             cls._lib = L
         return cls._lib
 

@@ -182,6 +182,54 @@ def test_int8_real_samples_vs_reference(oracle_lib, track_record):
         assert oc.sum() > 1200  # five active channels, one dump per code period
 
 
+@pytest.mark.parametrize("form,packed", [(0, True), (0, False), (1, False), (2, True), (3, True)])
+def test_glonass_channels_closed_loop(oracle_lib, form, packed):
+    """GLONASS channels in the integer correlator (the reference's hooks put to use, include/gnssb200.h): two GPS and two
+    GLONASS satellites (frequency channels -3 and +2, IF 1 MHz + k * 562.5 kHz) in one record; PRN register 1<<10
+    selects the ST code and the 1022-half-chip period, chan.system the GLONASS reference words.  Search (1021 delays),
+    confirm, pull-in on every kernel form, both sample formats: all dump records and the final state equal the oracle's."""
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+    from gnss_sdr_ru_b200.lib import default_cfg
+    from gnss_sdr_ru_b200.synth import Sat, make_record, pack2
+
+    nblk = 700
+    sats = [Sat(prn=27, doppler_hz=1200, cn0_dbhz=50, code_phase_chips=1000.3, data_seed=5),
+            Sat(prn=9, doppler_hz=-900, cn0_dbhz=47, code_phase_chips=980.0, data_seed=6),
+            Sat(system="glonass", prn=-3, doppler_hz=1150, cn0_dbhz=50, code_phase_chips=490.2, data_seed=7, data_rate_hz=100.0),
+            Sat(system="glonass", prn=2, doppler_hz=-950, cn0_dbhz=48, code_phase_chips=480.0, data_seed=8, data_rate_hz=100.0)]
+    rec = make_record(sats, NS * nblk, seed=77)
+    G = abi.PRN_GLONASS
+    prns = [27, G, 0, 9, 0, G, 0, 0, 0, G, 0, 5]
+    fch = {1: -3, 5: 2, 9: 6}  # channel -> frequency channel (k = 6 carries no signal)
+    warm = {0: 1, 3: -1, 1: 1, 5: -1}
+    over = dict(glonass_carrier_if=1.0e6, tic_period=0.0171)
+    eng = TrackingEngine(n_streams=1, cfg=default_cfg(**over))
+    o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(**over))
+    eng.simple_cold_allocate(0, prns)
+    o.cold_allocate(prns)
+    step = int(562500.0 / (5 * 16e6 / 2**30))
+    assert step == 7549747  # the firmware's GLNS_L1_CARR_REF_STEP
+    for ch, k in fch.items():
+        eng.set_glonass_channel(0, ch, k)
+        o.rx.chan[ch].carrier_cold_corr = k * step
+        o.ch_carrier(ch, o.cfg.glonass_carrier_ref + k * step)
+    for ch, nf in warm.items():
+        eng.warm_start(0, ch, nf)
+        kk = o.rx.chan[ch]
+        kk.n_freq, kk.del_freq, kk.codes = nf, (-2 * nf if nf > 0 else 1 - 2 * nf), 0
+        kk.carrier_freq = (o.cfg.glonass_carrier_ref if kk.system else o.cfg.gps_carrier_ref) + kk.carrier_cold_corr + o.cfg.d_freq * nf
+        o.ch_carrier(ch, kk.carrier_freq)
+    assert _rx_bytes(eng.rx[0]) == _rx_bytes(o.rx)
+    eng.upload()
+    eng.set_track_variant(form, 0)
+    dumps, cnt = _compare_run(eng, [o], rec[None, :], nblk, fmt=abi.FMT_PACKED2 if packed else abi.FMT_INT8_IQ,
+                              packed=pack2(rec)[None, :] if packed else None, cap=1200)
+    assert cnt[0, 1] > 340 and cnt[0, 0] > 340  # both codes last 1 ms: 1022 half chips at 511 kHz, 2046 at 1.023 MHz
+    states = [int(eng.rx[0].chan[ch].state) for ch in range(12)]
+    assert states[1] >= 3 and states[5] >= 3 and states[0] >= 3 and states[3] >= 3, states  # found, confirmed, pulling in / tracking
+    assert states[9] == 1  # no satellite on that frequency channel: still searching
+
+
 def test_closed_loop_multi_stream(oracle_lib, track_record):
     rec, _ = track_record
     n, S = 250, 5
