@@ -13,10 +13,6 @@
 #pragma once
 #include "track_common.cuh"
 
-#ifndef SEG_UNROLL
-#define SEG_UNROLL 1
-#endif
-
 struct __align__(16) BlockParams {
   uint32_t cph0, kph0, cinc, kinc;
   uint32_t hc0, w1, stale_idx, stale_bits;
