@@ -220,8 +220,8 @@ int gnssb200_acq_serial(gnssb200_handle *h, const void *d_if, int fmt, int64_t n
 
 /* Scheduling knob of the tracking kernel: the blocks of every channel are cut into slices of `blocks`
  * blocks that are handed to CTAs through a work queue (keeps all SMs busy whatever the channel count).
- * 0 = automatic (slices of 128 blocks -- 512 KB of packed samples, so the slices in flight stay L2 resident -- from four channels per SM on, one slice per channel below).  Results do
- * not depend on it. */
+ * 0 = automatic (slices of 512 KB of samples per stream -- 128 blocks of packed, 32 of int8 input -- so the slices in
+ * flight stay L2 resident, from four channels per SM on; one slice per channel below).  Results do not depend on it. */
 int gnssb200_set_track_slice(gnssb200_handle *h, int64_t blocks);
 
 /* Which form of the tracking kernel runs (results do not depend on it; tests and A/B measurements use it).
