@@ -53,6 +53,8 @@ struct AcqWorkspace {
   size_t cls_cap = 0;
   gnssb200_acq_row *d_out_tmp = nullptr;  // for the host convenience call
   size_t out_cap = 0;
+  uint8_t *d_iq_stage = nullptr;  // record staging of gnssb200_acq_pcps_host, kept between calls
+  size_t iq_cap = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -295,6 +297,7 @@ void acq_free_workspace(gnssb200_handle *h) {
   cudaFree(w->d_rows);
   cudaFree(w->d_cls_inc);
   cudaFree(w->d_out_tmp);
+  cudaFree(w->d_iq_stage);
   delete w;
   h->acq_ws = nullptr;
 }
@@ -520,12 +523,28 @@ extern "C" int gnssb200_acq_pcps_host(gnssb200_handle *h, const gnssb200_acq_cfg
   if (!h || !cfg) return -10;
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t bytes = fmt == GNSSB200_FMT_INT8_IQ ? (size_t)n_samples * 2 : (size_t)n_samples / 2;
-  uint8_t *d_iq = nullptr;
-  CUDA_TRY(cudaMalloc(&d_iq, bytes + 16));
-  CUDA_TRY(cudaMemcpy(d_iq, h_iq, bytes, cudaMemcpyHostToDevice));
+  if (!h->acq_ws) h->acq_ws = new AcqWorkspace();
+  AcqWorkspace &w = *(AcqWorkspace *)h->acq_ws;
   const int total = cfg->n_sv * gnssb200_acq_num_bins(cfg);
-  gnssb200_acq_row *d_rows = nullptr;
-  CUDA_TRY(cudaMalloc(&d_rows, sizeof(gnssb200_acq_row) * total));
+  if (total <= 0 || n_samples <= 0 || !h_iq) return -10;
+  // staging buffers live in the handle: no allocation (and no implicit device synchronisation of a free) per call
+  if (bytes + 16 > w.iq_cap) {
+    cudaFree(w.d_iq_stage);
+    w.d_iq_stage = nullptr;
+    w.iq_cap = 0;
+    CUDA_TRY(cudaMalloc(&w.d_iq_stage, bytes + 16));
+    w.iq_cap = bytes + 16;
+  }
+  if (sizeof(gnssb200_acq_row) * (size_t)total > w.out_cap) {
+    cudaFree(w.d_out_tmp);
+    w.d_out_tmp = nullptr;
+    w.out_cap = 0;
+    CUDA_TRY(cudaMalloc(&w.d_out_tmp, sizeof(gnssb200_acq_row) * (size_t)total));
+    w.out_cap = sizeof(gnssb200_acq_row) * (size_t)total;
+  }
+  uint8_t *d_iq = w.d_iq_stage;
+  gnssb200_acq_row *d_rows = w.d_out_tmp;
+  CUDA_TRY(cudaMemcpy(d_iq, h_iq, bytes, cudaMemcpyHostToDevice));
   int rc = gnssb200_acq_search(h, cfg, d_iq, fmt, n_samples, d_rows, nullptr);
   std::vector<gnssb200_acq_row> rows(total);
   if (!rc) {
@@ -535,8 +554,6 @@ extern "C" int gnssb200_acq_pcps_host(gnssb200_handle *h, const gnssb200_acq_cfg
       rc = (int)e;
     }
   }
-  cudaFree(d_iq);
-  cudaFree(d_rows);
   if (rc) return rc;
   if (h_rows_opt) memcpy(h_rows_opt, rows.data(), sizeof(gnssb200_acq_row) * total);
   gnssb200_acq_finalize(cfg, rows.data(), results);
