@@ -339,6 +339,72 @@ def test_dropin_random_registers(oracle_lib, nsamp, tic):
             _poke(rng, put, o, b)
 
 
+@pytest.mark.parametrize("form", [3, 2, 0])
+def test_batched_random_registers(oracle_lib, form):
+    """Random register traffic between short batched runs on packed input (the segment kernel when form = 3): code NCO
+    words inside, at the edges of and far outside the 7-or-8-samples range, carrier words, small and large slews, PRN
+    changes (GLONASS code included), epoch loads, TIC latches on; the loop is closed on the device (ISR running).
+    After every run the whole receiver state (both register files, correlator and channel state) equals the oracle's."""
+    from gnss_sdr_ru_b200.lib import default_cfg
+    from gnss_sdr_ru_b200.receiver import TrackingEngine
+    from gnss_sdr_ru_b200.synth import pack2
+
+    rng = np.random.default_rng(100 + form)
+    over = dict(tic_period=0.0037, acq_thresh=1500)
+    eng = TrackingEngine(n_streams=1, cfg=default_cfg(**over))
+    o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(**over))
+    prns = [27, 3, abi.PRN_GLONASS, 31, 32, 1, 0, 12, 9, 0, 32, 5]
+    eng.simple_cold_allocate(0, prns)
+    o.cold_allocate(prns)
+    ref_code = int(o.cfg.gps_code_ref)
+    edges = [int(2**29 / 80) - 1, int(2**29 / 80) + 1, int(2**32 / 7 / 80), int(2**32 / 7 / 80) + 1]  # kinc = 80 * word
+    L = eng.L
+
+    def both(fn_eng, fn_orc):
+        fn_eng()
+        fn_orc()
+
+    for it in range(160):
+        nblk = int(rng.integers(1, 6))
+        iq = rng.choice(np.array([-3, -1, 1, 3], dtype=np.int8), size=2 * NS * nblk)
+        for _ in range(int(rng.integers(0, 4))):
+            ch = int(rng.integers(0, 12))
+            kind = int(rng.integers(0, 7))
+            if kind == 0:
+                v = int(rng.choice([0, 1, 7, 32, 33, abi.PRN_GLONASS, 27]))
+                both(lambda: eng.ch_cntl(0, ch, v), lambda: o.ch_cntl(ch, v))
+            elif kind == 1:
+                v = int(o.cfg.gps_carrier_ref + rng.integers(-70000, 70000))
+                both(lambda: eng.ch_carrier(0, ch, v), lambda: o.ch_carrier(ch, v))
+            elif kind == 2:
+                v = int(rng.choice([ref_code + int(rng.integers(-3000, 3000)), ref_code // 2, int(rng.choice(edges)), ref_code * int(rng.integers(2, 20))]))
+                both(lambda: eng.ch_code(0, ch, v), lambda: o.ch_code(ch, v))
+            elif kind == 3:
+                v = int(rng.integers(0, 5))
+                both(lambda: L.gnssb200_ch_code_slew(C.byref(eng.rx[0]), ch, v), lambda: o.ch_code_slew(ch, v))
+            elif kind == 4:
+                v = int(rng.integers(0, 50 * 256))
+                both(lambda: L.gnssb200_ch_epoch_load(C.byref(eng.rx[0]), ch, v), lambda: o.ch_epoch_load(ch, v))
+            elif kind == 5 and it % 5 == 0:
+                v = int(rng.integers(0, 3000))
+                both(lambda: L.gnssb200_ch_code_slew(C.byref(eng.rx[0]), ch, v), lambda: o.ch_code_slew(ch, v))
+        assert _rx_bytes(eng.rx[0]) == _rx_bytes(o.rx), f"host-side register helpers differ at iteration {it}"
+        eng.upload()
+        eng.set_track_variant(form, 0)
+        eng.run_host(pack2(iq)[None, :], nblk, NS, abi.FMT_PACKED2, dump_cap=0)
+        eng.download()
+        n, _, _ = o.run(iq, NS, nblk)
+        if n < nblk:  # the oracle stopped like the reference (CHANNEL_OFF with a dump): so did the device
+            assert eng.rx[0].halted
+            break
+        got, want = eng.rx[0], o.rx
+        for name, _ in abi.Rx._fields_:
+            ga, wa = getattr(got, name), getattr(want, name)
+            gb = bytes(memoryview(ga).cast("B")) if hasattr(ga, "_length_") or isinstance(ga, C.Structure) else ga
+            wb = bytes(memoryview(wa).cast("B")) if hasattr(wa, "_length_") or isinstance(wa, C.Structure) else wa
+            assert gb == wb, f"iteration {it} ({nblk} blocks): rx.{name} differs"
+
+
 def test_closed_loop_vs_reference_golden():
     """GPU vs the committed outputs of the compiled reference itself (tests/golden/ref_track_golden.npz)"""
     import os
