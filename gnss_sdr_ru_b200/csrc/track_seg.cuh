@@ -18,7 +18,7 @@ struct __align__(16) BlockParams {
   uint32_t hc0, w1, stale_idx, stale_bits;
   int mode, event;
   uint32_t wtot;  // code-NCO wraps over the block = index of the tail segment
-  uint32_t seg;   // 1: the segment form applies (kinc in range)
+  uint32_t seg;   // segment form that applies to the block's code NCO word: 1 = 7 or 8 samples per half chip, 2 = 15 or 16, 0 = neither
   double dinv;    // 1.0 / kinc, correctly rounded
   double pad;
 };
@@ -33,6 +33,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // the sample whose step wraps, n = ceil((2^32 - ks) / kinc); n >= 7 for all ks < kinc iff 7*kinc <= 2^32, n <= 8 iff
 // 8*kinc >= 2^32
 __device__ __forceinline__ bool seg_kinc_ok(uint32_t kinc) { return kinc >= (1u << 29) && 7ull * kinc <= (1ull << 32); }
+// the same with 15 or 16 samples per half chip (the 511-kHz GLONASS ST code at 16 Msps: 15.66)
+__device__ __forceinline__ bool seg_kinc_ok16(uint32_t kinc) { return kinc >= (1u << 28) && 15ull * kinc <= (1ull << 32); }
 
 // first sample of segment m >= 1: s = ceil((m*2^32 - kph0) / kinc) = floor((x - 0.5) / kinc) + 1 with x = m*2^32 -
 // kph0 >= 1.  In doubles: x - 0.5 is exact (x < 2^44), (x - 0.5)/kinc is at least 0.5/kinc > 2^-31 away from every
@@ -119,6 +121,65 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
   accL = aL;
 }
 
+// The same for code NCO rates with 15 or 16 samples per half chip (GLONASS channels): sixteen 4-bit codes per segment
+// from three aligned words, the sixteenth sample conditional.  k15 = 15 * kinc.
+template <int H>
+__device__ __forceinline__ void correlate_segments16(uint32_t q, uint32_t cph, uint32_t ks, const uint32_t cinc, const uint32_t kinc,
+                                                     const uint32_t k15, const uint32_t hp, const int nvalid, const uint32_t vlut_lane,
+                                                     const PipeK K, int &accE, int &accP, int &accL, const SegBounds bnd) {
+  int aE = 0, aP = 0, aL = 0;
+  TCHECK(0, ks < kinc || nvalid == 0);
+  TCHECK(1, hp >= bnd.bits_lo && hp + 4u * (H + 1) <= bnd.bits_hi + 4u);
+  uint32_t hq = hp;
+  const uint32_t hq_valid = hp + 4u * (uint32_t)nvalid;
+  const uint32_t hq_end = hp + 4u * (uint32_t)H;
+#pragma unroll 1
+  do {
+    const uint32_t a = (q >> 3) & ~3u;
+    TCHECK(2, a >= bnd.tile_lo && a + 12u <= bnd.tile_hi);
+    const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
+    const uint32_t t = lds_u32(hq);
+    const uint32_t wd[2] = {__funnelshift_r(w0, w1, q), __funnelshift_r(w1, w2, q)};
+    uint32_t u, c;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(u), "=r"(c) : "r"(ks), "r"(k15));
+    const uint32_t e16 = K.k1 - c;  // 1: sixteen samples
+    ks = e16 * kinc + u;
+    q = e16 * 4u + (q + 60u);
+    int S = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        uint32_t sh;
+        if (k == 0)
+          sh = wd[half] << 7;
+        else if (k == 1)
+          sh = wd[half] << 3;
+        else
+          sh = wd[half] >> (4 * k - 7);
+        uint32_t ca;
+        asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(ca) : "r"(sh), "r"(vlut_lane));
+        const uint32_t eaddr = (cph >> 29) * K.k2048 + ca;
+        TCHECK(3, eaddr >= bnd.vlut_lo && eaddr + 4u <= bnd.vlut_hi);
+        v[k] = (int)lds_u32(eaddr);
+        if (half == 0 || k < 7) cph += cinc;
+      }
+      S += ((v[0] + v[1] + v[2]) + (v[3] + v[4] + v[5])) + v[6] + (half == 0 ? v[7] : (int)e16 * v[7]);
+    }
+    cph = e16 * cinc + cph;
+    if (hq < hq_valid) {
+      aE += sext8(t, 0) * S;
+      aP += sext8(t, 1) * S;
+      aL += sext8(t, 2) * S;
+    }
+    hq += 4u;
+  } while (hq != hq_end);
+  accE = aE;
+  accP = aP;
+  accL = aL;
+}
+
 // One sample from the closed forms (SURVEY.md Appendix A rules A2-A6) into the A (up to the dump) or B sums.
 struct SampleCtx {
   uint32_t cph0, kph0, cinc, kinc, hc0, w1, stale_idx;
@@ -156,7 +217,7 @@ __device__ __forceinline__ void eval_sample(const SampleCtx &c, int i, int (&sum
 // 1 + tid*H ... ; a thread whose run contains the dump keeps the part before it and hands the rest to thread NT-1
 // (which has no segments of its own), so every thread's sums belong to one side of the dump.  Warp 0 evaluates the
 // head segment and whatever follows the owned segments (the tail) one sample per lane.
-template <int NT, int H>
+template <int NT, int H, int SLOTS = 8>
 __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx &sc, const uint32_t tile_addr, const uint32_t tbl_addr,
                                           const uint32_t alias_addr, const uint32_t vlut_lane, const PipeK K, const int nsamp,
                                           const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB, const SegBounds bnd_in) {
@@ -202,10 +263,14 @@ __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx 
     bnd.bits_lo = alias_addr;
     bnd.bits_hi = alias_addr + 4u * 48u;
   }
-  TCHECK(4, nv == 0 || s + 7u * nv <= (uint32_t)nsamp);  // owned segments lie inside the block
+  TCHECK(4, nv == 0 || s + (uint32_t)(SLOTS - 1) * nv <= (uint32_t)nsamp);  // owned segments lie inside the block
   int pE, pP, pL;
-  correlate_segments<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 7u * p.kinc, hp, (int)nv,
-                        vlut_lane, K, pE, pP, pL, bnd);
+  if constexpr (SLOTS == 16)
+    correlate_segments16<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 15u * p.kinc, hp, (int)nv,
+                            vlut_lane, K, pE, pP, pL, bnd);
+  else
+    correlate_segments<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 7u * p.kinc, hp, (int)nv,
+                          vlut_lane, K, pE, pP, pL, bnd);
   {
     int v[6];
     unpack_lanes(pL, v[0], v[1]);

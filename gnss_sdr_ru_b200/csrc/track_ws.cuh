@@ -249,13 +249,14 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
       p.mode = sp.mode; p.event = event ? 1 : 0;
       if constexpr (SEGH > 0) {
         if (sp.mode == MODE_FAST) {
-          const bool ok = seg_kinc_ok(sp.kinc);
+          const uint32_t form = seg_kinc_ok(sp.kinc) ? 1u : (seg_kinc_ok16(sp.kinc) ? 2u : 0u);
+          const bool ok = form != 0;
           if (ok && sp.kinc != inv_of) {  // the division only when the code NCO word changed
             dinv = 1.0 / (double)sp.kinc;
             inv_of = sp.kinc;
           }
           p.wtot = (uint32_t)(((unsigned long long)sp.kph0 + (unsigned long long)a.nsamp * sp.kinc) >> 32);
-          p.seg = ok ? 1u : 0u;
+          p.seg = form;
           p.dinv = dinv;
         }
       }
@@ -495,9 +496,13 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
 #else
                             smem_u32(vlut), smem_u32(vlut) + 128u * 32u * 4u};
 #endif
-        if (bp.seg)
+        constexpr int SEGH16 = (SEGH * 8 + 15) / 16;  // segments per thread at 15-16 samples each: (CT-1)*SEGH16 covers the ~522 of a block
+        if (bp.seg == 1)
           seg_block<CT, SEGH>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
                               PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
+        else if (bp.seg == 2)
+          seg_block<CT, SEGH16, 16>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
+                                    PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
         else
           generic_block<CT>(sc, a.nsamp, ctid, sumA, sumB, anyB);
       } else {

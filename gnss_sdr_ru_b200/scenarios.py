@@ -22,6 +22,7 @@ class TrackScenario:
     sats: list  # list[Sat], one per channel
     prns: list  # PRN per channel (12)
     n_freq: list  # warm-start Doppler bin per channel
+    fch: list = None  # GLONASS frequency channel per correlator channel (None: GPS scenario)
 
 
 def gps_tracking_scenario(seed: int, n_sats: int = 12, cn0=(46.0, 52.0)) -> TrackScenario:
@@ -76,11 +77,31 @@ def synth_sat_array(scenarios: list) -> tuple:
     return arr, n_sats
 
 
+def glonass_tracking_scenario(seed: int, n_sats: int = 12, cn0=(46.0, 52.0)) -> TrackScenario:
+    """Twelve GLONASS L1OF satellites on distinct frequency channels (k = -7..+6, IF 1 MHz + k * 562.5 kHz), one per
+    correlator channel of the integer receiver (PRN register abi.PRN_GLONASS), each warm-started in its Doppler bin."""
+    rng = np.random.default_rng(seed)
+    ks = [int(k) for k in rng.choice(np.arange(-7, 7), size=n_sats, replace=False)]
+    sats, bins = [], []
+    for i, k in enumerate(ks):
+        n = int(rng.integers(1, 5)) * (1 if rng.random() < 0.5 else -1)
+        fd = 1000.0 * n + float(rng.uniform(-300.0, 300.0))
+        cell = int(rng.integers(20, 300))  # half-chip search cell in which the serial search meets the code
+        theta = (511.0 - 0.5 * cell + float(rng.uniform(-0.1, 0.1))) % 511.0
+        sats.append(Sat(system="glonass", prn=k, cn0_dbhz=float(rng.uniform(*cn0)), doppler_hz=fd, code_phase_chips=theta,
+                        carrier_phase_cycles=float(rng.random()), data_seed=int(seed * 100 + i + 1), data_rate_hz=100.0))
+        bins.append(n)
+    return TrackScenario(sats=sats, prns=[abi.PRN_GLONASS] * n_sats + [0] * (abi.N_CHANNELS - n_sats),
+                         n_freq=bins + [0] * (abi.N_CHANNELS - n_sats), fch=ks + [0] * (abi.N_CHANNELS - n_sats))
+
+
 def apply_tracking_scenario(engine, stream: int, sc: TrackScenario) -> None:
     """simple_cold_allocate + per-channel warm start on a TrackingEngine host state."""
     engine.simple_cold_allocate(stream, sc.prns)
     for ch, (prn, n) in enumerate(zip(sc.prns, sc.n_freq)):
         if prn > 0:
+            if sc.fch is not None and prn == abi.PRN_GLONASS:
+                engine.set_glonass_channel(stream, ch, sc.fch[ch])
             engine.warm_start(stream, ch, n)
 
 

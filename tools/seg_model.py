@@ -20,7 +20,7 @@ def seg_start(m, kph0, kinc):
     return int(np.float64(x) * (np.float64(1.0) / np.float64(kinc))) + 1
 
 
-def seg_model(v, kph0, kinc, hc0, w1, stale_idx, tbl, n, NT, H):
+def seg_model(v, kph0, kinc, hc0, w1, stale_idx, tbl, n, NT, H, SLOTS=8):
     wtot = (kph0 + n * kinc) >> 32
     NF = wtot - 1 if wtot > 0 else 0
     A = B = 0
@@ -56,9 +56,9 @@ def seg_model(v, kph0, kinc, hc0, w1, stale_idx, tbl, n, NT, H):
         assert ks < kinc
         acc = 0
         for j in range(H):
-            u = ks + 7 * kinc
+            u = ks + (SLOTS - 1) * kinc
             eight = u < 2**32
-            cnt = 8 if eight else 7
+            cnt = SLOTS if eight else SLOTS - 1
             ks = (u + (kinc if eight else 0)) % 2**32
             if j < nv:
                 assert s + cnt <= n
@@ -102,6 +102,15 @@ def main():
             a = brute(v, kph0, kinc, hc0, w1, stale_idx, tbl, n)
             b = seg_model(v, kph0, kinc, hc0, w1, stale_idx, tbl, n, NT, H)
             assert a == b, (it, n, kinc, kph0, hc0, w1, NT, H, a, b)
+        # 15 or 16 samples per half chip (GLONASS channels): H = 6 / 3 / 2 segments per thread
+        kinc16 = int(rng.integers(2**28, 2**32 // 15 + 1)) if it % 3 else 274340960 + int(rng.integers(-2000, 2000))
+        wtot16 = (kph0 + n * kinc16) >> 32
+        w1b = 1022 - hc0 % 1022 if mode == 0 else int(rng.integers(1, max(2, wtot16 + 3)))
+        hc0b = hc0 % 1022
+        for NT, H in ((96, 6), (192, 3), (384, 2)):
+            a = brute(v, kph0, kinc16, hc0b, w1b, hc0b + w1b, tbl, n)
+            b = seg_model(v, kph0, kinc16, hc0b, w1b, hc0b + w1b, tbl, n, NT, H, SLOTS=16)
+            assert a == b, ("16", it, n, kinc16, kph0, hc0b, w1b, NT, H, a, b)
     print("segment partition model: ok")
 
 
