@@ -250,6 +250,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     if (h->device < 0 || h->device >= 64 || !aws[h->device]) {
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
+      CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<5, GNSSB200_FMT_INT8_IQ, 96, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_I8));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<2, GNSSB200_FMT_PACKED2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<3, GNSSB200_FMT_PACKED2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
       CUDA_TRY(cudaFuncSetAttribute(track_ws_kernel<1, GNSSB200_FMT_PACKED2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, DSM_PK));
@@ -303,7 +304,7 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
     // Half-chip segments need 7 or 8 samples per half chip: decided from the nominal code NCO word of this
     // configuration (a block whose word left that range is still handled, sample by sample, inside the kernel).
     bool seg = false;
-    if (fmt == GNSSB200_FMT_PACKED2 && form != 2) {
+    if ((fmt == GNSSB200_FMT_PACKED2 || fmt == GNSSB200_FMT_INT8_IQ) && form != 2) {
       const int shk = 32 - h->cfg.code_nco_bits;
       if (shk >= 0 && shk < 32) {
         const long long w = (long long)((double)((long long)h->cfg.gps_code_ref << shk) * h->cfg.clock_mult);  // gp2021.c:100-118
@@ -324,7 +325,9 @@ int track_launch(gnssb200_handle *h, int first_stream, int n_streams, const void
       if (form >= 3) seg = true;  // forced: out-of-range blocks take the per-sample form inside the kernel
     }
     const size_t dyn_seg = dyn + 2048;  // slack to start the mixer table on a 2048-byte boundary
-    if (fmt == GNSSB200_FMT_INT8_IQ && per_sm >= 3)
+    if (fmt == GNSSB200_FMT_INT8_IQ && seg && (form == 0 || form == 3))  // segment form on int8 I,Q samples; 224 bytes of read-ahead behind the second tile
+      track_ws_kernel<5, GNSSB200_FMT_INT8_IQ, 96, 11><<<items, 128, dyn + 256, st>>>(a, tile_bytes);
+    else if (fmt == GNSSB200_FMT_INT8_IQ && per_sm >= 3)
       track_ws_kernel<3, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);
     else if (fmt == GNSSB200_FMT_INT8_IQ)
       track_ws_kernel<2, GNSSB200_FMT_INT8_IQ, 256><<<items, 288, dyn, st>>>(a, tile_bytes);

@@ -121,6 +121,60 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
   accL = aL;
 }
 
+// The segment loop on int8 I,Q samples (the reference's own file format, 2 bytes per sample, any int8 value): the
+// mixer is the reference's two multiplications per output (correlator.c:214-215) with the LO pair
+// (ival + 65536*qval coefficients of I and Q, fill_lo_lut) read from an 8-entry shared table -- one LDS.64, two
+// PRMT sign extensions, two IMADs per sample -- and the three code multiplications once per half chip as above.
+// q = bit address of the sample's I byte (8 * tile address + 16*s): a segment's 16 bytes come from five aligned words.
+template <int H>
+__device__ __forceinline__ void correlate_segments_i8(uint32_t q, uint32_t cph, uint32_t ks, const uint32_t cinc, const uint32_t kinc,
+                                                      const uint32_t k7, const uint32_t hp, const int nvalid, const uint32_t lut_addr,
+                                                      const PipeK K, int &accE, int &accP, int &accL, const SegBounds bnd) {
+  int aE = 0, aP = 0, aL = 0;
+  TCHECK(0, ks < kinc || nvalid == 0);
+  TCHECK(1, hp >= bnd.bits_lo && hp + 4u * (H + 1) <= bnd.bits_hi + 4u);
+  uint32_t hq = hp;
+  const uint32_t hq_valid = hp + 4u * (uint32_t)nvalid;
+  const uint32_t hq_end = hp + 4u * (uint32_t)H;
+#pragma unroll 1
+  do {
+    const uint32_t a = (q >> 3) & ~3u;
+    TCHECK(2, a >= bnd.tile_lo && a + 20u <= bnd.tile_hi);
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = lds_u32(a + 4u * i);
+    const uint32_t t = lds_u32(hq);
+    uint32_t x[4];  // eight samples as (I0, Q0, I1, Q1) bytes: the window starts on a word or in its middle
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[i] = __funnelshift_r(w[i], w[i + 1], q);
+    uint32_t u, c;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(u), "=r"(c) : "r"(ks), "r"(k7));
+    const uint32_t e8 = K.k1 - c;
+    ks = e8 * kinc + u;
+    q = e8 * 16u + (q + 112u);
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int I = sext8(x[k >> 1], (k & 1) * 2), Q = sext8(x[k >> 1], (k & 1) * 2 + 1);
+      uint32_t lx, ly;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lx), "=r"(ly) : "r"((cph >> 29) * K.k8 + lut_addr));
+      v[k] = I * (int)lx + Q * (int)ly;  // ival + 65536*qval
+      if (k < 7) cph += cinc;
+    }
+    cph = e8 * cinc + cph;
+    const int S = (int)e8 * v[7] + (((v[0] + v[1] + v[2]) + (v[3] + v[4] + v[5])) + v[6]);
+    if (hq < hq_valid) {
+      aE += sext8(t, 0) * S;
+      aP += sext8(t, 1) * S;
+      aL += sext8(t, 2) * S;
+    }
+    hq += 4u;
+  } while (hq != hq_end);
+  accE = aE;
+  accP = aP;
+  accL = aL;
+}
+
 // The same for code NCO rates with 15 or 16 samples per half chip (GLONASS channels): sixteen 4-bit codes per segment
 // from three aligned words, the sixteenth sample conditional.  k15 = 15 * kinc.
 template <int H>
@@ -217,7 +271,7 @@ __device__ __forceinline__ void eval_sample(const SampleCtx &c, int i, int (&sum
 // 1 + tid*H ... ; a thread whose run contains the dump keeps the part before it and hands the rest to thread NT-1
 // (which has no segments of its own), so every thread's sums belong to one side of the dump.  Warp 0 evaluates the
 // head segment and whatever follows the owned segments (the tail) one sample per lane.
-template <int NT, int H, int SLOTS = 8>
+template <int NT, int H, int SLOTS = 8, bool I8 = false>
 __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx &sc, const uint32_t tile_addr, const uint32_t tbl_addr,
                                           const uint32_t alias_addr, const uint32_t vlut_lane, const PipeK K, const int nsamp,
                                           const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB, const SegBounds bnd_in) {
@@ -265,7 +319,10 @@ __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx 
   }
   TCHECK(4, nv == 0 || s + (uint32_t)(SLOTS - 1) * nv <= (uint32_t)nsamp);  // owned segments lie inside the block
   int pE, pP, pL;
-  if constexpr (SLOTS == 16)
+  if constexpr (I8)  // vlut_lane carries the shared address of the LO table here
+    correlate_segments_i8<H>(8u * tile_addr + 16u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 7u * p.kinc, hp, (int)nv,
+                             vlut_lane, K, pE, pP, pL, bnd);
+  else if constexpr (SLOTS == 16)
     correlate_segments16<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 15u * p.kinc, hp, (int)nv,
                             vlut_lane, K, pE, pP, pL, bnd);
   else

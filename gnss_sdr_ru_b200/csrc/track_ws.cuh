@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
   constexpr int WS_THREADS = WS_CORR_THREADS + 32;
   constexpr int fmt = FMT;
   constexpr bool packed_native = FMT == GNSSB200_FMT_PACKED2;
-  static_assert(SEGH == 0 || FMT == GNSSB200_FMT_PACKED2, "the segment form reads packed samples");
+  static_assert(SEGH == 0 || FMT == GNSSB200_FMT_PACKED2 || FMT == GNSSB200_FMT_INT8_IQ, "the segment form reads packed or int8 I,Q samples");
   __shared__ ChanShared cs;
   __shared__ BlockParams params[2];
   __shared__ uint2 lut[8];
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
       p.mode = sp.mode; p.event = event ? 1 : 0;
       if constexpr (SEGH > 0) {
         if (sp.mode == MODE_FAST) {
-          const uint32_t form = seg_kinc_ok(sp.kinc) ? 1u : (seg_kinc_ok16(sp.kinc) ? 2u : 0u);
+          const uint32_t form = seg_kinc_ok(sp.kinc) ? 1u : ((packed_native && seg_kinc_ok16(sp.kinc)) ? 2u : 0u);
           const bool ok = form != 0;
           if (ok && sp.kinc != inv_of) {  // the division only when the code NCO word changed
             dinv = 1.0 / (double)sp.kinc;
@@ -490,21 +490,32 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
         const SampleCtx sc{cph0, kph0, cinc, kinc, hc0, w1, stale_idx, tile, tbl, lut, fmt};
         // what the segment loop may read: the tile plus the 48 bytes idle trailing segments run past it (the other tile or
         // the mixer table follow), the code-table window, the mixer table
-        const SegBounds bnd{smem_u32(tile), smem_u32(tile) + (uint32_t)tile_bytes + 64u, smem_u32(tbl), smem_u32(tbl) + 4u * SMEM_TBL,
+        const SegBounds bnd{smem_u32(tile), smem_u32(tile) + (uint32_t)tile_bytes + (packed_native ? 64u : 224u), smem_u32(tbl), smem_u32(tbl) + 4u * SMEM_TBL,
 #ifdef TRACK_CHECK_SELFTEST  // a deliberately wrong bound: the check must fire (tools/gpu_evidence.sh)
                             smem_u32(vlut), smem_u32(vlut) + 64u * 32u * 4u};
 #else
                             smem_u32(vlut), smem_u32(vlut) + 128u * 32u * 4u};
 #endif
         constexpr int SEGH16 = (SEGH * 8 + 15) / 16;  // segments per thread at 15-16 samples each: (CT-1)*SEGH16 covers the ~522 of a block
-        if (bp.seg == 1)
-          seg_block<CT, SEGH>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
-                              PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
-        else if (bp.seg == 2)
-          seg_block<CT, SEGH16, 16>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
-                                    PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
-        else
-          generic_block<CT>(sc, a.nsamp, ctid, sumA, sumB, anyB);
+        bool done = false;
+        if constexpr (packed_native) {
+          if (bp.seg == 1) {
+            seg_block<CT, SEGH>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
+                                PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
+            done = true;
+          } else if (bp.seg == 2) {
+            seg_block<CT, SEGH16, 16>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
+                                      PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
+            done = true;
+          }
+        } else {
+          if (bp.seg == 1) {  // int8 I,Q samples: the LO table instead of the mixer table
+            seg_block<CT, SEGH, 8, true>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), smem_u32(lut),
+                                         PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
+            done = true;
+          }
+        }
+        if (!done) generic_block<CT>(sc, a.nsamp, ctid, sumA, sumB, anyB);
       } else {
         uint32_t cur[SPT / 2];
         uint32_t pk[SPT / 8];

@@ -129,6 +129,20 @@ def test_packed_kernel_forms(oracle_lib, track_record, form, occ, ns):
     _compare_run(eng, orcs, recs, nblk, fmt=abi.FMT_PACKED2, packed=np.stack([pack2(r) for r in recs]), cap=1200, ns=ns)
 
 
+@pytest.mark.parametrize("ns", [8192, 4000, 8160, 64])
+def test_int8_segment_form(oracle_lib, track_record, ns):
+    """The half-chip-segment loop on int8 I,Q samples (the reference's own file format): search with slews and false
+    alarms, confirm, pull-in, tracking, TIC latches, three streams -- records and final state equal the oracle's."""
+    rec, _ = track_record
+    nblk = 420 if ns >= 4000 else 2500
+    S = 3
+    over = dict(tic_period=0.0123, acq_thresh=1100)
+    recs = np.stack([np.roll(rec[: 2 * ns * nblk], 2 * 1013 * s) for s in range(S)])
+    eng, orcs = _setup_pair(oracle_lib, n_streams=S, cfg_over=over)
+    eng.set_track_variant(3, 0)
+    _compare_run(eng, orcs, recs, nblk, fmt=abi.FMT_INT8_IQ, cap=1200, ns=ns)
+
+
 def test_segment_form_other_code_rates(oracle_lib, track_record):
     """The half-chip-segment kernel with code NCO words outside its 7-or-8-samples range (twice and 0.9 times the
     C/A rate on some channels, set through the configuration and through per-channel register writes): those blocks
@@ -339,8 +353,8 @@ def test_dropin_random_registers(oracle_lib, nsamp, tic):
             _poke(rng, put, o, b)
 
 
-@pytest.mark.parametrize("form", [3, 2, 0])
-def test_batched_random_registers(oracle_lib, form):
+@pytest.mark.parametrize("form,packed", [(3, True), (2, True), (0, True), (3, False)])
+def test_batched_random_registers(oracle_lib, form, packed):
     """Random register traffic between short batched runs on packed input (the segment kernel when form = 3): code NCO
     words inside, at the edges of and far outside the 7-or-8-samples range, carrier words, small and large slews, PRN
     changes (GLONASS code included), epoch loads, TIC latches on; the loop is closed on the device (ISR running).
@@ -349,7 +363,7 @@ def test_batched_random_registers(oracle_lib, form):
     from gnss_sdr_ru_b200.receiver import TrackingEngine
     from gnss_sdr_ru_b200.synth import pack2
 
-    rng = np.random.default_rng(100 + form)
+    rng = np.random.default_rng(100 + form + (0 if packed else 50))
     over = dict(tic_period=0.0037, acq_thresh=1500)
     eng = TrackingEngine(n_streams=1, cfg=default_cfg(**over))
     o = oracle_lib.Oracle(oracle_lib.Oracle.default_cfg(**over))
@@ -367,6 +381,8 @@ def test_batched_random_registers(oracle_lib, form):
     for it in range(160):
         nblk = int(rng.integers(1, 6))
         iq = rng.choice(np.array([-3, -1, 1, 3], dtype=np.int8), size=2 * NS * nblk)
+        if not packed and it % 9 == 0:
+            iq = rng.integers(-128, 128, size=2 * NS * nblk).astype(np.int8)  # any int8 works
         for _ in range(int(rng.integers(0, 4))):
             ch = int(rng.integers(0, 12))
             kind = int(rng.integers(0, 7))
@@ -391,7 +407,10 @@ def test_batched_random_registers(oracle_lib, form):
         assert _rx_bytes(eng.rx[0]) == _rx_bytes(o.rx), f"host-side register helpers differ at iteration {it}"
         eng.upload()
         eng.set_track_variant(form, 0)
-        eng.run_host(pack2(iq)[None, :], nblk, NS, abi.FMT_PACKED2, dump_cap=0)
+        if packed:
+            eng.run_host(pack2(iq)[None, :], nblk, NS, abi.FMT_PACKED2, dump_cap=0)
+        else:
+            eng.run_host(iq[None, :], nblk, NS, abi.FMT_INT8_IQ, dump_cap=0)
         eng.download()
         n, _, _ = o.run(iq, NS, nblk)
         if n < nblk:  # the oracle stopped like the reference (CHANNEL_OFF with a dump): so did the device
