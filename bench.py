@@ -170,8 +170,10 @@ def run_reference(args):
     # (gnss_sdr_ru_b200/synth.py) inside each worker -- nothing in this process tree loads libgnssb200.so or CUDA.
     ctx = get_context("fork")
     times = []
-    with ctx.Pool(workers) as pool:
-        pool.map(_ref_make_record, [(i, nblk) for i in range(workers)])  # each worker keeps the record of its stream
+    with ctx.Pool(workers) as pool:  # records first, in parallel, handed back to this process ...
+        for i, r in enumerate(pool.map(_ref_make_record, [(i, nblk) for i in range(workers)], chunksize=1)):
+            _REF_RECORDS[i] = r
+    with ctx.Pool(workers) as pool:  # ... so that the workers forked now all inherit every record
         for it in range(args.warmup + args.steps):
             res = pool.map(_ref_worker, [(i, nblk) for i in range(workers)], chunksize=1)
             dt = max(r for r in res)  # processing time of the slowest worker
@@ -207,8 +209,7 @@ def _ref_record(i, nblk):
 
 
 def _ref_make_record(job):
-    _ref_record(*job)
-    return 0
+    return _ref_record(*job)
 
 
 def _ref_worker(job):
