@@ -20,8 +20,24 @@ struct __align__(16) BlockParams {
   uint32_t wtot;  // code-NCO wraps over the block = index of the tail segment
   uint32_t seg;   // segment form that applies to the block's code NCO word: 1 = 7 or 8 samples per half chip, 2 = 15 or 16, 0 = neither
   double dinv;    // 1.0 / kinc, correctly rounded
-  double pad;
+  uint32_t kseg;  // (samples per full segment - 1) * kinc: the addend whose carry tells a short segment from a long one
+  uint32_t pad;
 };
+static_assert(sizeof(BlockParams) == 64, "BlockParams: four 16-byte rows");
+
+// Build knobs of the 8-slot segment loop (A/B builds: EXTRA_NVCC_FLAGS=-DSEG_U2=0, tools/ab_variants.sh).
+// SEG_U2 = 1: two segments per loop round -- no register move of the prefetched table entry, half the loop control
+// and half the re-loads of the kernel parameters k1 / k2048: 78 -> 75 instructions per segment, 1.84 -> 1.93 M
+// channel*Msamples/s at 64 streams.  SEG_PIN = 1: the loop's three run-time constants (7*kinc, k1, k2048) read from
+// shared memory through volatile loads, so that ptxas cannot re-create them inside the loop (it does, to save
+// registers: three issue slots per segment); 73 instructions per segment, but 8 bytes of spills at the 80-register
+// cap of six resident CTAs -- measured slower (1.91 M with SEG_U2, 1.82 M without), kept as a knob only.
+#ifndef SEG_U2
+#define SEG_U2 1
+#endif
+#ifndef SEG_PIN  // the volatile reads (measured on their own and with the paired rounds: 1.3 % / 1.0 % slower -- off)
+#define SEG_PIN 0
+#endif
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t t;
@@ -54,7 +70,9 @@ struct SegBounds {  // shared-memory windows the loop may touch (TRACK_CHECK bui
 template <int H>
 __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uint32_t ks, const uint32_t cinc, const uint32_t kinc,
                                                    const uint32_t k7, const uint32_t hp, const int nvalid, const uint32_t vlut_lane,
-                                                   const PipeK K, int &accE, int &accP, int &accL, const SegBounds bnd) {
+                                                   const PipeK K, int &accE, int &accP, int &accL, const SegBounds bnd,
+                                                   const uint32_t kseg_addr /* shared: this block's 7*kinc */,
+                                                   const uint32_t kconst_addr /* shared: {k1, k2048} */) {
   int aE = 0, aP = 0, aL = 0;
   TCHECK(0, ks < kinc || nvalid == 0);                                    // a run starts on a code-NCO wrap
   TCHECK(1, hp >= bnd.bits_lo && hp + 4u * (H + 1) <= bnd.bits_hi + 4u);  // code-table entries of the run (+ one read ahead)
@@ -72,50 +90,79 @@ __device__ __forceinline__ void correlate_segments(uint32_t q, uint32_t cph, uin
   uint32_t hq = hp;                                      // running table address: the loop counter
   const uint32_t hq_valid = hp + 4u * (uint32_t)nvalid;  // segments at or past it do not count
   const uint32_t hq_end = hp + 4u * (uint32_t)H;
+#if SEG_PIN
+  uint32_t k7r, k1r, k2048r;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(k7r) : "r"(kseg_addr));
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k1r), "=r"(k2048r) : "r"(kconst_addr));
+  TCHECK(0, k7r == k7 && k1r == K.k1 && k2048r == K.k2048);
+#else
+  const uint32_t k7r = k7, k1r = K.k1, k2048r = K.k2048;
+#endif
+  // one segment: tc = its code-table entry (fetched a segment earlier), tn receives the next one
+#define SEG_BODY(tc, tn)                                                                                             \
+  {                                                                                                                  \
+    /* eight 4-bit sample codes from bit address q (two aligned words, funnel shift by q mod 32) */                  \
+    const uint32_t wd = __funnelshift_r(lo, hi, q);                                                                  \
+    /* 7 or 8 samples: the segment ends with the sample whose code step wraps; e8 = 1 when there are eight */        \
+    uint32_t u, c;                                                                                                   \
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(u), "=r"(c) : "r"(ks), "r"(k7r));                    \
+    const uint32_t e8 = k1r - c;                                                                                     \
+    ks = e8 * kinc + u;                                                                                              \
+    q = e8 * 4u + (q + 28u);                                                                                         \
+    /* next segment's words and table entry (one segment past the run in the last round: still inside the windows) */ \
+    const uint32_t a = (q >> 3) & ~3u;                                                                               \
+    TCHECK(2, a >= bnd.tile_lo && a + 8u <= bnd.tile_hi); /* sample window inside the tile (+ read-ahead slack) */   \
+    lo = lds_u32(a);                                                                                                 \
+    hi = lds_u32(a + 4);                                                                                             \
+    tn = lds_u32(hq + 4u);                                                                                           \
+    int v[8];                                                                                                        \
+    _Pragma("unroll") for (int k = 0; k < 8; k++) {                                                                  \
+      /* entry offset = (phase*16 + code) * 128 bytes + lane*4 */                                                    \
+      uint32_t sh;                                                                                                   \
+      if (k == 0)                                                                                                    \
+        sh = wd << 7;                                                                                                \
+      else if (k == 1)                                                                                               \
+        sh = wd << 3;                                                                                                \
+      else                                                                                                           \
+        sh = wd >> (4 * k - 7);                                                                                      \
+      uint32_t ca;                                                                                                   \
+      asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(ca) : "r"(sh), "r"(vlut_lane)); /* (sh & 0x780) | vlut_lane */  \
+      const uint32_t eaddr = (cph >> 29) * k2048r + ca; /* LO phase = top three bits of the carrier NCO */           \
+      TCHECK(3, eaddr >= bnd.vlut_lo && eaddr + 4u <= bnd.vlut_hi); /* mixer table entry */                          \
+      v[k] = (int)lds_u32(eaddr);                                                                                    \
+      if (k < 7) cph += cinc;                                                                                        \
+    }                                                                                                                \
+    cph = e8 * cinc + cph;                                                                                           \
+    const int S = (int)e8 * v[7] + (((v[0] + v[1] + v[2]) + (v[3] + v[4] + v[5])) + v[6]);                           \
+    if (hq < hq_valid) {                                                                                             \
+      aE += sext8(tc, 0) * S;                                                                                        \
+      aP += sext8(tc, 1) * S;                                                                                        \
+      aL += sext8(tc, 2) * S;                                                                                        \
+    }                                                                                                                \
+    hq += 4u;                                                                                                        \
+  }
+#if SEG_U2
+  uint32_t t2;
+  if (H & 1) {  // an odd run length: one segment ahead of the pairs
+    SEG_BODY(t, t2)
+    t = t2;
+  }
+  if (H > 1) {
+#pragma unroll 1
+    do {
+      SEG_BODY(t, t2)
+      SEG_BODY(t2, t)
+    } while (hq != hq_end);
+  }
+#else
 #pragma unroll 1
   do {
-    // eight 4-bit sample codes from bit address q (two aligned words, funnel shift by q mod 32)
-    const uint32_t wd = __funnelshift_r(lo, hi, q);
-    // 7 or 8 samples: the segment ends with the sample whose code step wraps; e8 = 1 when there are eight
-    uint32_t u, c;
-    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(u), "=r"(c) : "r"(ks), "r"(k7));
-    const uint32_t e8 = K.k1 - c;
-    ks = e8 * kinc + u;
-    q = e8 * 4u + (q + 28u);
-    // next segment's words and table entry (one segment past the run in the last round: still inside the windows)
-    const uint32_t a = (q >> 3) & ~3u;
-    TCHECK(2, a >= bnd.tile_lo && a + 8u <= bnd.tile_hi);  // sample window inside the tile (+ read-ahead slack)
-    lo = lds_u32(a);
-    hi = lds_u32(a + 4);
-    const uint32_t t_next = lds_u32(hq + 4u);
-    int v[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      // entry offset = (phase*16 + code) * 128 bytes + lane*4
-      uint32_t sh;
-      if (k == 0)
-        sh = wd << 7;
-      else if (k == 1)
-        sh = wd << 3;
-      else
-        sh = wd >> (4 * k - 7);
-      uint32_t ca;
-      asm("lop3.b32 %0, %1, 0x780, %2, 0xEA;" : "=r"(ca) : "r"(sh), "r"(vlut_lane));  // (sh & 0x780) | vlut_lane
-      const uint32_t eaddr = (cph >> 29) * K.k2048 + ca;  // LO phase = top three bits of the carrier NCO
-      TCHECK(3, eaddr >= bnd.vlut_lo && eaddr + 4u <= bnd.vlut_hi);  // mixer table entry
-      v[k] = (int)lds_u32(eaddr);
-      if (k < 7) cph += cinc;
-    }
-    cph = e8 * cinc + cph;
-    const int S = (int)e8 * v[7] + (((v[0] + v[1] + v[2]) + (v[3] + v[4] + v[5])) + v[6]);
-    if (hq < hq_valid) {
-      aE += sext8(t, 0) * S;
-      aP += sext8(t, 1) * S;
-      aL += sext8(t, 2) * S;
-    }
+    uint32_t t_next;
+    SEG_BODY(t, t_next)
     t = t_next;
-    hq += 4u;
   } while (hq != hq_end);
+#endif
+#undef SEG_BODY
   accE = aE;
   accP = aP;
   accL = aL;
@@ -274,7 +321,8 @@ __device__ __forceinline__ void eval_sample(const SampleCtx &c, int i, int (&sum
 template <int NT, int H, int SLOTS = 8, bool I8 = false>
 __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx &sc, const uint32_t tile_addr, const uint32_t tbl_addr,
                                           const uint32_t alias_addr, const uint32_t vlut_lane, const PipeK K, const int nsamp,
-                                          const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB, const SegBounds bnd_in) {
+                                          const int ptid, int (&sumA)[6], int (&sumB)[6], bool &anyB, const SegBounds bnd_in,
+                                          const uint32_t kseg_addr = 0, const uint32_t kconst_addr = 0) {
   // Which run of segments a thread owns: consecutive runs start 43 bytes apart in the tile (H = 11), i.e. lanes l and
   // l+3 of a warp would read the same bank (4-way conflicts on the two window loads of every segment); stepping
   // through the runs with stride 7 spreads a warp over the banks (2-way).
@@ -327,7 +375,7 @@ __device__ __forceinline__ void seg_block(const BlockParams &p, const SampleCtx 
                             vlut_lane, K, pE, pP, pL, bnd);
   else
     correlate_segments<H>(8u * tile_addr + 4u * s, p.cph0 + s * p.cinc, p.kph0 + s * p.kinc, p.cinc, p.kinc, 7u * p.kinc, hp, (int)nv,
-                          vlut_lane, K, pE, pP, pL, bnd);
+                          vlut_lane, K, pE, pP, pL, bnd, kseg_addr, kconst_addr);
   {
     int v[6];
     unpack_lanes(pL, v[0], v[1]);

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
   __shared__ uint32_t tbl[SMEM_TBL];
   __shared__ uint32_t alias_tbl[2][48];  // per ring slot: tbl[0..47] with entry 0 = the block's stale bits (rule A6)
   __shared__ __align__(16) int totals[12];
+  __shared__ __align__(8) uint32_t kconst[2];  // {k1, k2048} for the segment loop's volatile reads (track_seg.cuh, SEG_U2)
   __shared__ __align__(8) uint64_t dfull[2], pfull[2], empty[2], tfull;
   extern __shared__ __align__(128) uint8_t tiles[];
   // mixer table behind the two tiles; the segment form ORs the sample code into the table address, so there the
@@ -145,6 +146,10 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
   SchedQueue *const wq = a.sched;
   // channel-independent tables first: they fill while the control lane may still be waiting for its item
   fill_lo_lut(lut);
+  if (tid == 0) {
+    kconst[0] = a.k1;
+    kconst[1] = a.k2048;
+  }
   if (packed_native) {
     for (int i = tid; i < 128 * 32; i += WS_THREADS) {
       const int e = i >> 5, ph = e >> 4, code = e & 15;
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
           p.wtot = (uint32_t)(((unsigned long long)sp.kph0 + (unsigned long long)a.nsamp * sp.kinc) >> 32);
           p.seg = form;
           p.dinv = dinv;
+          p.kseg = 7u * sp.kinc;
         }
       }
       alias_tbl[slot][0] = sp.stale_bits;
@@ -501,7 +507,8 @@ __global__ void __launch_bounds__(CT + 32, MINB) track_ws_kernel(const TrackArgs
         if constexpr (packed_native) {
           if (bp.seg == 1) {
             seg_block<CT, SEGH>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,
-                                PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd);
+                                PipeK{a.k1, a.k8, a.k128, a.k2048}, a.nsamp, ctid, sumA, sumB, anyB, bnd, smem_u32(&params[slot].kseg),
+                                smem_u32(kconst));
             done = true;
           } else if (bp.seg == 2) {
             seg_block<CT, SEGH16, 16>(bp, sc, smem_u32(tile), smem_u32(tbl), smem_u32(alias_tbl[slot]), vlut_lane,

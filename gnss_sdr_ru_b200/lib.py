@@ -13,7 +13,8 @@ import subprocess
 from . import abi
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(PKG_DIR, "libgnssb200.so")
+# GNSSB200_LIB: another build of the same library (A/B timing of kernel variants, tools/ab_variants.sh); still no CPU path
+SO_PATH = os.environ.get("GNSSB200_LIB") or os.path.join(PKG_DIR, "libgnssb200.so")
 
 _lib = None
 
