@@ -32,9 +32,10 @@ static_assert(sizeof(BlockParams) == 64, "BlockParams: four 16-byte rows");
 // shared memory through volatile loads, so that ptxas cannot re-create them inside the loop (it does, to save
 // registers: three issue slots per segment); 73 instructions per segment, but 8 bytes of spills at the 80-register
 // cap of six resident CTAs -- measured slower (1.91 M with SEG_U2, 1.82 M without), kept as a knob only.
-// Also measured and not kept: four segments per round (1.57 M: 525 instructions of loop code with the three leading
-// segments, the warps of a scheduler spread over it); two per round with an odd run entering at the second half
-// instead of a separate leading segment (1.82 M: the entry costs two branches and a reconvergence pair per round).
+// Also measured and not kept: three / four segments per round (1.65 / 1.57 M: 375 / 525 instructions of loop code with
+// the leading segments, the warps of a scheduler spread over it); two per round with an odd run entering at the second
+// half instead of a separate leading segment (1.82 M: the entry costs two branches and a reconvergence pair per
+// round) or running a twelfth, idle slot (1.83 M); the eighth-sample flag through add.cc / subc (spills).
 #ifndef SEG_U2
 #define SEG_U2 1
 #endif
