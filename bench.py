@@ -386,10 +386,13 @@ def run_ours(args):
         eng5 = TrackingEngine(n_streams=S5, device=local)
         scs5, d5 = scs[:S5], d_if[:S5]  # this rank's share: the first 64/N of the streams it already holds
 
+        for s in range(S5):
+            L.gnssb200_rx_init(C.byref(eng5.rx[s]), C.byref(eng5.cfg))
+            apply_tracking_scenario(eng5, s, scs5[s])
+        initial5 = bytes(eng5.rx)
+
         def step5():
-            for s in range(S5):
-                L.gnssb200_rx_init(C.byref(eng5.rx[s]), C.byref(eng5.cfg))
-                apply_tracking_scenario(eng5, s, scs5[s])
+            C.memmove(eng5.rx, initial5, len(initial5))
             eng5.upload()
             eng5.run_device(d5.data_ptr(), d5.stride(0), nblk, NS, fmt, stream=stream.cuda_stream)
 
